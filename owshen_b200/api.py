@@ -1,0 +1,363 @@
+"""ctypes binding of libowshen_b200.so and the host-side mirror of the API BASELINE.json's north_star
+names: prove() / verify() / MerkleTree.  The reference (OwshenNetwork/owshen @ c7b1f00) has no such
+API, so names and error behaviour follow its conventions instead: fallible
+calls raise (anyhow::Result -> exception), byte blobs are owned `bytes`, field elements are 32-byte
+little-endian (/root/reference/src/blockchain/tx/owshen_airdrop/babyjubjub/mod.rs:7-11).
+
+All hashing, witness generation, NTTs and MSMs run in the CUDA library; nothing here computes.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libowshen_b200.so")
+_lib = None
+
+FR_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+PROOF_BYTES = 256
+
+OG_OK, OG_E_VERIFY = 0, -6
+
+
+class OwshenB200Error(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = lib().og_strerror(code).decode() if _lib is not None else str(code)
+        super().__init__(f"owshen_b200 error {code}: {msg}" + (f" ({detail})" if detail else ""))
+
+
+def build_library(jobs=8):
+    """Compile every CUDA source for sm_100a into owshen_b200/libowshen_b200.so (in-tree)."""
+    subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), f"-j{jobs}"], check=True, stdout=subprocess.DEVNULL)
+
+
+_u8p = C.c_char_p
+_SIGS = {
+    "og_abi_version": (C.c_int32, []),
+    "og_strerror": (C.c_char_p, [C.c_int32]),
+    "og_last_error": (C.c_char_p, [C.c_void_p]),
+    "og_init": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "og_free": (None, [C.c_void_p]),
+    "og_sync": (C.c_int32, [C.c_void_p]),
+    "og_timer_start": (C.c_int32, [C.c_void_p]),
+    "og_timer_stop": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
+    "og_launch_count": (C.c_uint64, [C.c_void_p]),
+    "og_imad_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "og_field_op": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_mimc7_constants": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
+    "og_mimc7_hash2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_mimc7_merkle_paths": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "og_mimc7_merkle_paths_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "og_mimc7_merkle_build": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_msm_g1": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_msm_g2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_msm_g1_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_msm_g2_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_g1_sum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_g2_sum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_ntt": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32]),
+    "og_ntt_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32]),
+    "og_withdraw_r1cs_info": (C.c_int32, [C.c_uint32] + [C.POINTER(C.c_uint32)] * 4),
+    "og_withdraw_r1cs_export": (C.c_int32, [C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+    "og_withdraw_witness": (C.c_int32, [C.c_void_p, C.c_uint32] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p]),
+    "og_groth16_setup_withdraw": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_uint64)]),
+    "og_load_pk": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "og_free_pk": (None, [C.c_void_p]),
+    "og_pk_info": (C.c_int32, [C.c_void_p] + [C.POINTER(C.c_uint32)] * 4),
+    "og_groth16_prove": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "og_groth16_prove_withdraw": (C.c_int32, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "og_groth16_prove_withdraw_dev": (C.c_int32, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 5 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "og_groth16_h_evals": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "og_groth16_verify": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p]),
+}
+ABI_SYMBOLS = tuple(_SIGS)
+
+
+def lib():
+    """Load libowshen_b200.so; raises if the CUDA extension has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise OSError(f"{_LIB_PATH} is missing: build it with owshen_b200.build_library() / "
+                          "`make -C owshen_b200/csrc` -- there is no CPU fallback")
+        L = C.CDLL(_LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc, ctx=None):
+    if rc != OG_OK:
+        detail = ""
+        if ctx is not None and ctx._h:
+            detail = lib().og_last_error(ctx._h).decode(errors="replace")
+        raise OwshenB200Error(rc, detail)
+
+
+def _ptr(x):
+    """bytes / bytearray / int address / object with .ctypes or data_ptr() -> void*"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, (bytes, bytearray)):
+        return C.cast(C.c_char_p(bytes(x)) if isinstance(x, bytearray) else C.c_char_p(x), C.c_void_p)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    if hasattr(x, "ctypes"):
+        return C.c_void_p(x.ctypes.data)
+    return C.cast(x, C.c_void_p)
+
+
+def _bits_array(bits):
+    return (C.c_uint32 * len(bits))(*[int(b) & 0xFFFFFFFF for b in bits])
+
+
+def fr_bytes(x: int) -> bytes:
+    return (x % FR_MODULUS).to_bytes(32, "little")
+
+
+class Context:
+    """One CUDA device + one stream (og_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib().og_init(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().og_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def sync(self):
+        _check(lib().og_sync(self._h), self)
+
+    def timer_start(self):
+        _check(lib().og_timer_start(self._h), self)
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        _check(lib().og_timer_stop(self._h, C.byref(ms)), self)
+        return ms.value
+
+    @property
+    def launch_count(self) -> int:
+        return lib().og_launch_count(self._h)
+
+    def imad_peak(self):
+        a, b = C.c_double(), C.c_double()
+        _check(lib().og_imad_peak(self._h, C.byref(a), C.byref(b)), self)
+        return a.value, b.value
+
+    # ---- probes / kernels on host buffers -------------------------------------------------------
+    def field_op(self, field: str, op: str, a: bytes, b: bytes) -> bytes:
+        n = len(a) // 32
+        out = C.create_string_buffer(32 * n)
+        _check(lib().og_field_op(self._h, {"fq": 0, "fr": 1}[field], {"mul": 0, "add": 1, "sub": 2}[op], a, b, n, out), self)
+        return out.raw
+
+    def mimc7_hash2(self, left: bytes, right: bytes) -> bytes:
+        n = len(left) // 32
+        out = C.create_string_buffer(32 * n)
+        _check(lib().og_mimc7_hash2(self._h, left, right, n, out), self)
+        return out.raw
+
+    def merkle_paths(self, leaves: bytes, siblings: bytes, path_bits, depth: int) -> bytes:
+        n = len(leaves) // 32
+        assert len(siblings) == 32 * n * depth and len(path_bits) == n
+        out = C.create_string_buffer(32 * n * (depth + 1))
+        _check(lib().og_mimc7_merkle_paths(self._h, leaves, siblings, _bits_array(path_bits), n, depth, out), self)
+        return out.raw
+
+    def merkle_build(self, leaves: bytes) -> bytes:
+        n = len(leaves) // 32
+        out = C.create_string_buffer(32 * (2 * n - 1))
+        _check(lib().og_mimc7_merkle_build(self._h, leaves, n, out), self)
+        return out.raw
+
+    def msm_g1(self, points: bytes, scalars: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(points) == 64 * n
+        out = C.create_string_buffer(64)
+        _check(lib().og_msm_g1(self._h, points, scalars, n, out), self)
+        return out.raw
+
+    def msm_g2(self, points: bytes, scalars: bytes) -> bytes:
+        n = len(scalars) // 32
+        assert len(points) == 128 * n
+        out = C.create_string_buffer(128)
+        _check(lib().og_msm_g2(self._h, points, scalars, n, out), self)
+        return out.raw
+
+    def g1_sum(self, points: bytes) -> bytes:
+        out = C.create_string_buffer(64)
+        _check(lib().og_g1_sum(self._h, points, len(points) // 64, out), self)
+        return out.raw
+
+    def g2_sum(self, points: bytes) -> bytes:
+        out = C.create_string_buffer(128)
+        _check(lib().og_g2_sum(self._h, points, len(points) // 128, out), self)
+        return out.raw
+
+    def ntt(self, data: bytes, log_n: int, batch: int = 1, inverse=False, coset=False) -> bytes:
+        assert len(data) == (32 * batch) << log_n
+        buf = C.create_string_buffer(data, len(data))
+        _check(lib().og_ntt(self._h, buf, log_n, batch, int(inverse), int(coset)), self)
+        return buf.raw
+
+    def withdraw_witness(self, depth, nullifiers: bytes, secrets: bytes, recipients: bytes, siblings: bytes, path_bits) -> bytes:
+        n = len(nullifiers) // 32
+        nv = r1cs_info(depth)["n_vars"]
+        out = C.create_string_buffer(32 * n * nv)
+        _check(lib().og_withdraw_witness(self._h, depth, nullifiers, secrets, recipients, siblings, _bits_array(path_bits), n, out), self)
+        return out.raw
+
+
+def mimc7_constants():
+    out = C.create_string_buffer(32 * 91)
+    n = C.c_uint32()
+    _check(lib().og_mimc7_constants(out, C.byref(n)))
+    return [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(n.value)]
+
+
+def r1cs_info(depth: int) -> dict:
+    v = [C.c_uint32() for _ in range(4)]
+    _check(lib().og_withdraw_r1cs_info(depth, *[C.byref(x) for x in v]))
+    return dict(n_constraints=v[0].value, n_vars=v[1].value, n_pub=v[2].value, log_m=v[3].value)
+
+
+def r1cs_export(depth: int, which: str):
+    """(row_ptr, col_idx, coeffs as ints) of matrix 'A' | 'B' | 'C' of the product's withdraw R1CS."""
+    w = "ABC".index(which)
+    nnz = C.c_uint64()
+    _check(lib().og_withdraw_r1cs_export(depth, w, None, None, None, C.byref(nnz)))
+    nc = r1cs_info(depth)["n_constraints"]
+    ptr = (C.c_uint32 * (nc + 1))()
+    col = (C.c_uint32 * nnz.value)()
+    val = C.create_string_buffer(32 * nnz.value)
+    _check(lib().og_withdraw_r1cs_export(depth, w, ptr, col, val, C.byref(nnz)))
+    return list(ptr), list(col), [int.from_bytes(val.raw[32 * i:32 * i + 32], "little") for i in range(nnz.value)]
+
+
+def setup_withdraw(ctx: Context, depth: int, tau: int, alpha: int, beta: int, gamma: int, delta: int):
+    """Development setup (toxic waste supplied by the caller) -> (pk_bytes, vk_bytes)."""
+    toxic = b"".join(fr_bytes(x) for x in (tau, alpha, beta, gamma, delta))
+    pl, vl = C.c_uint64(), C.c_uint64()
+    _check(lib().og_groth16_setup_withdraw(ctx._h, depth, toxic, None, C.byref(pl), None, C.byref(vl)), ctx)
+    pk = C.create_string_buffer(pl.value)
+    vk = C.create_string_buffer(vl.value)
+    _check(lib().og_groth16_setup_withdraw(ctx._h, depth, toxic, pk, C.byref(pl), vk, C.byref(vl)), ctx)
+    return pk.raw[:pl.value], vk.raw[:vl.value]
+
+
+class ProvingKey:
+    """A proving key resident in HBM together with its fixed-base window tables (og_pk)."""
+
+    def __init__(self, ctx: Context, pk_bytes: bytes):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        _check(lib().og_load_pk(ctx._h, pk_bytes, len(pk_bytes), C.byref(self._h)), ctx)
+        v = [C.c_uint32() for _ in range(4)]
+        _check(lib().og_pk_info(self._h, *[C.byref(x) for x in v]))
+        self.n_vars, self.n_pub, self.log_m, self.depth = (x.value for x in v)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().og_free_pk(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def h_evals(self, witness: bytes) -> bytes:
+        out = C.create_string_buffer(32 << self.log_m)
+        _check(lib().og_groth16_h_evals(self.ctx._h, self._h, witness, out), self.ctx)
+        return out.raw
+
+    def prove_witnesses(self, witnesses: bytes, rs: bytes) -> bytes:
+        batch = len(rs) // 64
+        assert len(witnesses) == 32 * batch * self.n_vars
+        out = C.create_string_buffer(PROOF_BYTES * batch)
+        _check(lib().og_groth16_prove(self.ctx._h, self._h, witnesses, batch, rs, out), self.ctx)
+        return out.raw
+
+    def prove_withdraw(self, nullifiers, secrets, recipients, siblings, path_bits, rs, want_public=True):
+        """Host buffers in, host buffers out (H2D / D2H inside).  Buffers may be bytes or pinned
+        tensors / arrays exposing data_ptr() / .ctypes.  Returns (proofs, public_inputs)."""
+        batch = len(path_bits)
+        bits = path_bits if hasattr(path_bits, "data_ptr") or hasattr(path_bits, "ctypes") else _bits_array(path_bits)
+        proofs = C.create_string_buffer(PROOF_BYTES * batch)
+        pub = C.create_string_buffer(32 * self.n_pub * batch) if want_public else None
+        _check(lib().og_groth16_prove_withdraw(self.ctx._h, self._h, _ptr(nullifiers), _ptr(secrets), _ptr(recipients),
+                                               _ptr(siblings), _ptr(bits), batch, _ptr(rs), proofs, pub), self.ctx)
+        return proofs.raw, (pub.raw if want_public else None)
+
+
+def prove(pk: ProvingKey, nullifiers, secrets, recipients, siblings, path_bits, rs):
+    """prove(): batch of withdraw proofs from the secret inputs -> (proofs bytes, public inputs bytes)."""
+    return pk.prove_withdraw(nullifiers, secrets, recipients, siblings, path_bits, rs)
+
+
+def verify(vk_bytes: bytes, public_inputs: bytes, proof: bytes) -> bool:
+    """verify(): True / False for well-formed input, raises OwshenB200Error on malformed encodings."""
+    n_pub = len(public_inputs) // 32
+    rc = lib().og_groth16_verify(vk_bytes, len(vk_bytes), public_inputs, n_pub, proof)
+    if rc == OG_OK:
+        return True
+    if rc == OG_E_VERIFY:
+        return False
+    raise OwshenB200Error(rc)
+
+
+class MerkleTree:
+    """Fixed-depth sparse MiMC7 Merkle tree; every hash runs in the CUDA library.
+
+    insert_batch() appends leaves and rehashes only the touched ancestors, one batched
+    og_mimc7_hash2 launch per level.  path(i) returns (siblings bytes, path_bits int)."""
+
+    def __init__(self, ctx: Context, depth: int):
+        assert 1 <= depth <= 32
+        self.ctx, self.depth = ctx, depth
+        self.zeros = [bytes(32)]
+        for _ in range(depth):
+            self.zeros.append(ctx.mimc7_hash2(self.zeros[-1], self.zeros[-1]))
+        self.levels = [dict() for _ in range(depth + 1)]
+        self.n_leaves = 0
+
+    def _get(self, lvl, idx):
+        return self.levels[lvl].get(idx, self.zeros[lvl])
+
+    def insert_batch(self, leaves):
+        start = self.n_leaves
+        for k, leaf in enumerate(leaves):
+            self.levels[0][start + k] = leaf if isinstance(leaf, (bytes, bytearray)) else fr_bytes(leaf)
+        self.n_leaves += len(leaves)
+        dirty = sorted({(start + k) >> 1 for k in range(len(leaves))})
+        for lvl in range(self.depth):
+            left = b"".join(self._get(lvl, 2 * p) for p in dirty)
+            right = b"".join(self._get(lvl, 2 * p + 1) for p in dirty)
+            out = self.ctx.mimc7_hash2(left, right)
+            for k, p in enumerate(dirty):
+                self.levels[lvl + 1][p] = out[32 * k:32 * k + 32]
+            dirty = sorted({p >> 1 for p in dirty})
+        return list(range(start, start + len(leaves)))
+
+    def insert(self, leaf) -> int:
+        return self.insert_batch([leaf])[0]
+
+    def root(self) -> bytes:
+        return self._get(self.depth, 0)
+
+    def path(self, idx: int):
+        sibs, bits, i = [], 0, idx
+        for lvl in range(self.depth):
+            sibs.append(self._get(lvl, i ^ 1))
+            bits |= (i & 1) << lvl
+            i >>= 1
+        return b"".join(sibs), bits

@@ -1,0 +1,478 @@
+// owshen_b200/csrc/capi.cu -- the extern "C" boundary declared in include/owshen_b200.h.
+// Host-pointer entry points stage their buffers in persistent device slots (H2D/D2H on the ctx
+// stream, truly asynchronous when the caller's memory is pinned) and return after the result has
+// landed; `_dev` entry points only enqueue.  No entry point has a CPU implementation.
+#include "common.cuh"
+#include "groth16.cuh"
+#include "mimc.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+#include "withdraw_circuit.hpp"
+
+using namespace og;
+
+void* og_ctx::slot(int id, size_t bytes) {
+    if (bytes == 0) bytes = 32;
+    if (slot_cap[id] >= bytes) return slot_ptr[id];
+    cudaStreamSynchronize(stream);
+    if (slot_ptr[id]) cudaFree(slot_ptr[id]);
+    slot_ptr[id] = nullptr; slot_cap[id] = 0;
+    size_t cap = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&slot_ptr[id], cap);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(&slot_ptr[id], bytes);
+        cap = bytes;
+    }
+    if (e != cudaSuccess) {
+        snprintf(err, sizeof(err), "slot %d: cudaMalloc(%zu) failed: %s", id, bytes, cudaGetErrorString(e));
+        slot_ptr[id] = nullptr;
+        return nullptr;
+    }
+    slot_cap[id] = cap;
+    return slot_ptr[id];
+}
+
+namespace og {
+int32_t clear_flag(og_ctx* ctx) {
+    OG_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
+    return OG_OK;
+}
+int32_t check_flag(og_ctx* ctx) {
+    OG_CUDA(ctx, cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    OG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*ctx->h_flag) { snprintf(ctx->err, sizeof(ctx->err), "non-canonical field element in input"); return OG_E_ENCODING; }
+    return OG_OK;
+}
+}  // namespace og
+
+#define H2D(ctx, dst, src, bytes) OG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (ctx)->stream))
+#define D2H(ctx, dst, src, bytes) OG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (ctx)->stream))
+
+extern "C" {
+
+int32_t og_abi_version(void) { return 1; }
+
+const char* og_strerror(int32_t code) {
+    switch (code) {
+        case OG_OK: return "ok";
+        case OG_E_INVALID: return "invalid argument";
+        case OG_E_ENCODING: return "malformed or non-canonical encoding";
+        case OG_E_NO_DEVICE: return "no usable CUDA device (this library has no CPU path)";
+        case OG_E_CUDA: return "CUDA runtime error";
+        case OG_E_NOMEM: return "out of device memory";
+        case OG_E_VERIFY: return "proof does not verify";
+        default: return "unknown error";
+    }
+}
+const char* og_last_error(const og_ctx* ctx) { return ctx ? ctx->err : ""; }
+
+int32_t og_init(int32_t device, og_ctx** out) {
+    if (!out) return OG_E_INVALID;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return OG_E_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return OG_E_NO_DEVICE;
+    og_ctx* ctx = new og_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaMalloc(&ctx->d_flag, sizeof(int)) != cudaSuccess || cudaMallocHost(&ctx->h_flag, sizeof(int)) != cudaSuccess) {
+        delete ctx;
+        return OG_E_CUDA;
+    }
+    cudaMemset(ctx->d_flag, 0, sizeof(int));
+    int32_t rc = mimc_init(ctx);
+    if (rc != OG_OK) { og_free(ctx); return rc; }
+    *out = ctx;
+    return OG_OK;
+}
+
+void og_free(og_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < N_SLOTS; i++) if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
+    ntt_free_tables(ctx);
+    if (ctx->g1_fixed) cudaFree(ctx->g1_fixed);
+    if (ctx->g2_fixed) cudaFree(ctx->g2_fixed);
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int32_t og_sync(og_ctx* ctx) {
+    if (!ctx) return OG_E_INVALID;
+    OG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OG_OK;
+}
+int32_t og_timer_start(og_ctx* ctx) {
+    if (!ctx) return OG_E_INVALID;
+    OG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return OG_OK;
+}
+int32_t og_timer_stop(og_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return OG_E_INVALID;
+    OG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    OG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    OG_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return OG_OK;
+}
+uint64_t og_launch_count(const og_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- field probes --------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace og {
+template <class F>
+__global__ void __launch_bounds__(128) k_field_op(int op, const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint64_t n,
+                                                  uint8_t* __restrict__ out, int* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = load_canonical<F>(a + 32 * i, flag), y = load_canonical<F>(b + 32 * i, flag);
+    F r = op == 0 ? x * y : (op == 1 ? x + y : x - y);
+    store_canonical(out + 32 * i, r);
+}
+
+// integer-pipe micro-benchmark: long dependent-free chains of 32-bit multiply-adds
+template <int WIDE>
+__global__ void __launch_bounds__(256) k_imad(uint32_t* out, uint32_t iters, uint32_t seed) {
+    uint32_t a0 = threadIdx.x + seed, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3;
+    uint32_t x = blockIdx.x * 2654435761u + 12345u, y = x ^ 0x9e3779b9u;
+    if (WIDE) {
+        unsigned long long w0 = a0, w1 = a1, w2 = a2, w3 = a3, w4 = a0 ^ y, w5 = a1 ^ y, w6 = a2 ^ y, w7 = a3 ^ y;
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w0) : "r"(x), "r"(y));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w1) : "r"(x), "r"(y));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w2) : "r"(x), "r"(y));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w3) : "r"(x), "r"(y));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w4) : "r"(x), "r"(y));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w5) : "r"(x), "r"(y));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w6) : "r"(x), "r"(y));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w7) : "r"(x), "r"(y));
+            }
+        }
+        unsigned long long s = w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
+        if (s == 0x1234567ull) out[0] = (uint32_t)s;
+    } else {
+        uint32_t w0 = a0, w1 = a1, w2 = a2, w3 = a3, w4 = a0 ^ y, w5 = a1 ^ y, w6 = a2 ^ y, w7 = a3 ^ y;
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w0) : "r"(x), "r"(y));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w1) : "r"(x), "r"(y));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w2) : "r"(x), "r"(y));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w3) : "r"(x), "r"(y));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w4) : "r"(x), "r"(y));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w5) : "r"(x), "r"(y));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w6) : "r"(x), "r"(y));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w7) : "r"(x), "r"(y));
+            }
+        }
+        uint32_t s = w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
+        if (s == 0x1234567u) out[0] = s;
+    }
+}
+}  // namespace og
+
+extern "C" {
+
+int32_t og_imad_peak(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s) {
+    if (!ctx || !mad_per_s || !wide_mad_per_s) return OG_E_INVALID;
+    OG_SLOT(ctx, d_out, uint32_t, S_IO_A, 64);
+    const uint32_t iters = 4096, ctas = ctx->sm_count * 8, threads = 256;
+    const double ops = (double)ctas * threads * iters * 64.0;
+    float ms = 0;
+    for (int wide = 0; wide < 2; wide++) {
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            OG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+            if (wide) OG_LAUNCH(ctx, k_imad<1>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
+            else OG_LAUNCH(ctx, k_imad<0>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
+            OG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+            OG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+            OG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            double rate = ops / (ms * 1e-3);
+            if (rep > 0 && rate > best) best = rate;
+        }
+        if (wide) *wide_mad_per_s = best; else *mad_per_s = best;
+    }
+    return OG_OK;
+}
+
+int32_t og_field_op(og_ctx* ctx, int32_t field, int32_t op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
+    if (!ctx || !a || !b || !out || field < 0 || field > 1 || op < 0 || op > 2) return OG_E_INVALID;
+    if (n == 0) return OG_OK;
+    OG_SLOT(ctx, da, uint8_t, S_IO_A, 32 * n);
+    OG_SLOT(ctx, db, uint8_t, S_IO_B, 32 * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 32 * n);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, da, a, 32 * n); H2D(ctx, db, b, 32 * n);
+    unsigned grid = (unsigned)((n + 127) / 128);
+    if (field == 0) OG_LAUNCH(ctx, k_field_op<Fq>, grid, 128, 0, op, da, db, n, dout, ctx->d_flag);
+    else OG_LAUNCH(ctx, k_field_op<Fr>, grid, 128, 0, op, da, db, n, dout, ctx->d_flag);
+    D2H(ctx, out, dout, 32 * n);
+    return check_flag(ctx);
+}
+
+// ---- MiMC7 ----------------------------------------------------------------------------------------------
+int32_t og_mimc7_constants(uint8_t* out, uint32_t* n_rounds) {
+    if (!out || !n_rounds) return OG_E_INVALID;
+    Fr c[MIMC_ROUNDS];
+    mimc_constants_host(c);
+    for (int i = 0; i < MIMC_ROUNDS; i++) host_store(out + 32 * i, c[i]);
+    *n_rounds = MIMC_ROUNDS;
+    return OG_OK;
+}
+
+int32_t og_mimc7_hash2(og_ctx* ctx, const uint8_t* left, const uint8_t* right, uint64_t n, uint8_t* out) {
+    if (!ctx || !left || !right || !out) return OG_E_INVALID;
+    if (n == 0) return OG_OK;
+    OG_SLOT(ctx, da, uint8_t, S_IO_A, 32 * n);
+    OG_SLOT(ctx, db, uint8_t, S_IO_B, 32 * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 32 * n);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, da, left, 32 * n); H2D(ctx, db, right, 32 * n);
+    OG_TRY(mimc_hash2_dev(ctx, da, db, n, dout));
+    D2H(ctx, out, dout, 32 * n);
+    return check_flag(ctx);
+}
+
+int32_t og_mimc7_merkle_paths_dev(og_ctx* ctx, const uint8_t* d_leaves, const uint8_t* d_siblings, const uint32_t* d_path_bits,
+                                  uint32_t n_paths, uint32_t depth, uint8_t* d_out_nodes) {
+    if (!ctx || !d_leaves || !d_siblings || !d_path_bits || !d_out_nodes || depth > 32) return OG_E_INVALID;
+    return mimc_merkle_paths_dev(ctx, d_leaves, d_siblings, d_path_bits, n_paths, depth, d_out_nodes);
+}
+
+int32_t og_mimc7_merkle_paths(og_ctx* ctx, const uint8_t* leaves, const uint8_t* siblings, const uint32_t* path_bits,
+                              uint32_t n_paths, uint32_t depth, uint8_t* out_nodes) {
+    if (!ctx || !leaves || !siblings || !path_bits || !out_nodes || depth > 32) return OG_E_INVALID;
+    if (n_paths == 0) return OG_OK;
+    size_t nl = 32ull * n_paths, ns = 32ull * n_paths * depth, no = 32ull * n_paths * (depth + 1);
+    OG_SLOT(ctx, dl, uint8_t, S_IO_A, nl);
+    OG_SLOT(ctx, ds, uint8_t, S_IO_B, ns);
+    OG_SLOT(ctx, dbits, uint32_t, S_IO_C, 4ull * n_paths);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_D, no);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, dl, leaves, nl);
+    if (ns) H2D(ctx, ds, siblings, ns);
+    H2D(ctx, dbits, path_bits, 4ull * n_paths);
+    OG_TRY(mimc_merkle_paths_dev(ctx, dl, ds, dbits, n_paths, depth, dout));
+    D2H(ctx, out_nodes, dout, no);
+    return check_flag(ctx);
+}
+
+int32_t og_mimc7_merkle_build(og_ctx* ctx, const uint8_t* leaves, uint64_t n, uint8_t* out_levels) {
+    if (!ctx || !leaves || !out_levels || n == 0 || (n & (n - 1)) || n > (1ull << 28)) return OG_E_INVALID;
+    uint64_t total = 2 * n - 1;
+    OG_SLOT(ctx, din, uint8_t, S_IO_A, 32 * n);
+    OG_SLOT(ctx, lv, Fr, S_IO_B, sizeof(Fr) * total);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 32 * total);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, din, leaves, 32 * n);
+    OG_TRY(mimc_to_mont_dev(ctx, din, n, lv));
+    OG_TRY(mimc_tree_build_dev(ctx, lv, n));
+    OG_TRY(mimc_from_mont_dev(ctx, lv, total, dout));
+    D2H(ctx, out_levels, dout, 32 * total);
+    return check_flag(ctx);
+}
+
+// ---- MSM --------------------------------------------------------------------------------------------------
+int32_t og_msm_g1_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out64) {
+    if (!ctx || !d_out64 || (n && (!d_points || !d_scalars))) return OG_E_INVALID;
+    return msm_g1_dev(ctx, d_points, d_scalars, n, d_out64);
+}
+int32_t og_msm_g2_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out128) {
+    if (!ctx || !d_out128 || (n && (!d_points || !d_scalars))) return OG_E_INVALID;
+    return msm_g2_dev(ctx, d_points, d_scalars, n, d_out128);
+}
+int32_t og_msm_g1(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out64) {
+    if (!ctx || !out64 || (n && (!points || !scalars))) return OG_E_INVALID;
+    OG_SLOT(ctx, dp, uint8_t, S_IO_A, 64 * n);
+    OG_SLOT(ctx, ds, uint8_t, S_IO_B, 32 * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 64);
+    OG_TRY(clear_flag(ctx));
+    if (n) { H2D(ctx, dp, points, 64 * n); H2D(ctx, ds, scalars, 32 * n); }
+    OG_TRY(msm_g1_dev(ctx, dp, ds, n, dout));
+    D2H(ctx, out64, dout, 64);
+    return check_flag(ctx);
+}
+int32_t og_msm_g2(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out128) {
+    if (!ctx || !out128 || (n && (!points || !scalars))) return OG_E_INVALID;
+    OG_SLOT(ctx, dp, uint8_t, S_IO_A, 128 * n);
+    OG_SLOT(ctx, ds, uint8_t, S_IO_B, 32 * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 128);
+    OG_TRY(clear_flag(ctx));
+    if (n) { H2D(ctx, dp, points, 128 * n); H2D(ctx, ds, scalars, 32 * n); }
+    OG_TRY(msm_g2_dev(ctx, dp, ds, n, dout));
+    D2H(ctx, out128, dout, 128);
+    return check_flag(ctx);
+}
+int32_t og_g1_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out64) {
+    if (!ctx || !out64 || (n && !points)) return OG_E_INVALID;
+    OG_SLOT(ctx, dp, uint8_t, S_IO_A, 64 * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 64);
+    OG_TRY(clear_flag(ctx));
+    if (n) H2D(ctx, dp, points, 64 * n);
+    OG_TRY(sum_g1_dev(ctx, dp, n, dout));
+    D2H(ctx, out64, dout, 64);
+    return check_flag(ctx);
+}
+int32_t og_g2_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out128) {
+    if (!ctx || !out128 || (n && !points)) return OG_E_INVALID;
+    OG_SLOT(ctx, dp, uint8_t, S_IO_A, 128 * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 128);
+    OG_TRY(clear_flag(ctx));
+    if (n) H2D(ctx, dp, points, 128 * n);
+    OG_TRY(sum_g2_dev(ctx, dp, n, dout));
+    D2H(ctx, out128, dout, 128);
+    return check_flag(ctx);
+}
+
+// ---- NTT ----------------------------------------------------------------------------------------------------
+int32_t og_ntt_dev(og_ctx* ctx, uint8_t* d_data, uint32_t log_n, uint32_t batch, int32_t inverse, int32_t coset) {
+    if (!ctx || !d_data || log_n > 27 || !aligned32(d_data)) return OG_E_INVALID;
+    uint64_t tot = (uint64_t)batch << log_n;
+    if (tot == 0) return OG_OK;
+    OG_SLOT(ctx, work, Fr, S_NTT_DATA, sizeof(Fr) * tot * 2);
+    OG_TRY(mimc_to_mont_dev(ctx, d_data, tot, work));
+    OG_TRY(ntt_mont_dev(ctx, work, work + tot, log_n, batch, inverse, coset));
+    return mimc_from_mont_dev(ctx, work, tot, d_data);
+}
+int32_t og_ntt(og_ctx* ctx, uint8_t* data, uint32_t log_n, uint32_t batch, int32_t inverse, int32_t coset) {
+    if (!ctx || !data || log_n > 27) return OG_E_INVALID;
+    uint64_t tot = (uint64_t)batch << log_n;
+    if (tot == 0) return OG_OK;
+    OG_SLOT(ctx, dd, uint8_t, S_IO_A, 32 * tot);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, dd, data, 32 * tot);
+    OG_TRY(og_ntt_dev(ctx, dd, log_n, batch, inverse, coset));
+    D2H(ctx, data, dd, 32 * tot);
+    return check_flag(ctx);
+}
+
+// ---- withdraw statement ----------------------------------------------------------------------------------------
+int32_t og_withdraw_r1cs_info(uint32_t depth, uint32_t* n_constraints, uint32_t* n_vars, uint32_t* n_pub, uint32_t* log_m) {
+    if (depth == 0 || depth > 32) return OG_E_INVALID;
+    WithdrawLayout L = WithdrawLayout::make(depth);
+    if (n_constraints) *n_constraints = L.n_constraints;
+    if (n_vars) *n_vars = L.n_vars;
+    if (n_pub) *n_pub = WITHDRAW_N_PUB;
+    if (log_m) *log_m = groth16_domain_log(L.n_constraints, WITHDRAW_N_PUB);
+    return OG_OK;
+}
+int32_t og_withdraw_r1cs_export(uint32_t depth, int32_t which, uint32_t* row_ptr, uint32_t* col_idx, uint8_t* coeffs, uint64_t* nnz) {
+    if (depth == 0 || depth > 32 || which < 0 || which > 2 || !nnz) return OG_E_INVALID;
+    R1cs cs = WithdrawBuilder::build(depth);
+    const Csr& M = which == 0 ? cs.A : (which == 1 ? cs.B : cs.C);
+    *nnz = M.col.size();
+    if (!row_ptr || !col_idx || !coeffs) return OG_OK;
+    memcpy(row_ptr, M.row_ptr.data(), 4 * M.row_ptr.size());
+    memcpy(col_idx, M.col.data(), 4 * M.col.size());
+    for (size_t i = 0; i < M.val.size(); i++) host_store(coeffs + 32 * i, M.val[i]);
+    return OG_OK;
+}
+int32_t og_withdraw_witness(og_ctx* ctx, uint32_t depth, const uint8_t* nullifiers, const uint8_t* secrets, const uint8_t* recipients,
+                            const uint8_t* siblings, const uint32_t* path_bits, uint32_t batch, uint8_t* witnesses) {
+    if (!ctx || depth == 0 || depth > 32 || !nullifiers || !secrets || !recipients || !siblings || !path_bits || !witnesses) return OG_E_INVALID;
+    if (batch == 0) return OG_OK;
+    WithdrawLayout L = WithdrawLayout::make(depth);
+    OG_SLOT(ctx, dn, uint8_t, S_IO_A, 32ull * batch);
+    OG_SLOT(ctx, dsx, uint8_t, S_IO_B, 32ull * batch);
+    OG_SLOT(ctx, dr, uint8_t, S_IO_C, 32ull * batch);
+    OG_SLOT(ctx, dsib, uint8_t, S_IO_D, 32ull * batch * depth);
+    OG_SLOT(ctx, dbits, uint32_t, S_IO_E, 4ull * batch);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_F, 32ull * batch * L.n_vars);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, dn, nullifiers, 32ull * batch); H2D(ctx, dsx, secrets, 32ull * batch); H2D(ctx, dr, recipients, 32ull * batch);
+    H2D(ctx, dsib, siblings, 32ull * batch * depth); H2D(ctx, dbits, path_bits, 4ull * batch);
+    OG_TRY(withdraw_witness_bytes_dev(ctx, depth, dn, dsx, dr, dsib, dbits, batch, dout));
+    D2H(ctx, witnesses, dout, 32ull * batch * L.n_vars);
+    return check_flag(ctx);
+}
+
+// ---- Groth16 -------------------------------------------------------------------------------------------------------
+int32_t og_groth16_setup_withdraw(og_ctx* ctx, uint32_t depth, const uint8_t* toxic160, uint8_t* pk_out, uint64_t* pk_len,
+                                  uint8_t* vk_out, uint64_t* vk_len) {
+    if (!ctx || !pk_len || !vk_len || ((pk_out || vk_out) && !toxic160)) return OG_E_INVALID;
+    return setup_withdraw(ctx, depth, toxic160, pk_out, pk_len, vk_out, vk_len);
+}
+int32_t og_load_pk(og_ctx* ctx, const uint8_t* pk_bytes, uint64_t len, og_pk** out) {
+    if (!ctx || !pk_bytes || !out) return OG_E_INVALID;
+    return pk_load(ctx, pk_bytes, len, out);
+}
+void og_free_pk(og_pk* pk) { pk_free(pk); }
+int32_t og_pk_info(const og_pk* pk, uint32_t* n_vars, uint32_t* n_pub, uint32_t* log_m, uint32_t* depth) {
+    if (!pk) return OG_E_INVALID;
+    pk_info(pk, n_vars, n_pub, log_m, depth);
+    return OG_OK;
+}
+
+int32_t og_groth16_prove(og_ctx* ctx, const og_pk* pk, const uint8_t* witnesses, uint32_t batch, const uint8_t* rs, uint8_t* proofs) {
+    if (!ctx || !pk || !witnesses || !rs || !proofs) return OG_E_INVALID;
+    if (batch == 0) return OG_OK;
+    uint32_t nv; pk_info(pk, &nv, nullptr, nullptr, nullptr);
+    OG_SLOT(ctx, dw, uint8_t, S_IO_A, 32ull * batch * nv);
+    OG_SLOT(ctx, drs, uint8_t, S_IO_B, 64ull * batch);
+    OG_SLOT(ctx, dpr, uint8_t, S_IO_C, 256ull * batch);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, dw, witnesses, 32ull * batch * nv); H2D(ctx, drs, rs, 64ull * batch);
+    OG_TRY(prove_witness_dev(ctx, pk, dw, batch, drs, dpr));
+    D2H(ctx, proofs, dpr, 256ull * batch);
+    return check_flag(ctx);
+}
+
+int32_t og_groth16_prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_nullifiers, const uint8_t* d_secrets,
+                                      const uint8_t* d_recipients, const uint8_t* d_siblings, const uint32_t* d_path_bits, uint32_t batch,
+                                      const uint8_t* d_rs, uint8_t* d_proofs, uint8_t* d_public_out) {
+    if (!ctx || !pk || !d_nullifiers || !d_secrets || !d_recipients || !d_siblings || !d_path_bits || !d_rs || !d_proofs) return OG_E_INVALID;
+    return prove_withdraw_dev(ctx, pk, d_nullifiers, d_secrets, d_recipients, d_siblings, d_path_bits, batch, d_rs, d_proofs, d_public_out);
+}
+
+int32_t og_groth16_prove_withdraw(og_ctx* ctx, const og_pk* pk, const uint8_t* nullifiers, const uint8_t* secrets, const uint8_t* recipients,
+                                  const uint8_t* siblings, const uint32_t* path_bits, uint32_t batch, const uint8_t* rs, uint8_t* proofs,
+                                  uint8_t* public_out) {
+    if (!ctx || !pk || !nullifiers || !secrets || !recipients || !siblings || !path_bits || !rs || !proofs) return OG_E_INVALID;
+    if (batch == 0) return OG_OK;
+    uint32_t depth, n_pub; pk_info(pk, nullptr, &n_pub, nullptr, &depth);
+    if (depth == 0) return OG_E_INVALID;
+    OG_SLOT(ctx, dn, uint8_t, S_IO_A, 32ull * batch);
+    OG_SLOT(ctx, dsx, uint8_t, S_IO_B, 32ull * batch);
+    OG_SLOT(ctx, dr, uint8_t, S_IO_C, 32ull * batch);
+    OG_SLOT(ctx, dsib, uint8_t, S_IO_D, 32ull * batch * depth);
+    OG_SLOT(ctx, dbits, uint32_t, S_IO_E, 4ull * batch);
+    OG_SLOT(ctx, drs, uint8_t, S_IO_F, 64ull * batch);
+    OG_SLOT(ctx, dpr, uint8_t, S_IO_G, 256ull * batch);
+    OG_SLOT(ctx, dpub, uint8_t, S_IO_H, 32ull * batch * n_pub);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, dn, nullifiers, 32ull * batch); H2D(ctx, dsx, secrets, 32ull * batch); H2D(ctx, dr, recipients, 32ull * batch);
+    H2D(ctx, dsib, siblings, 32ull * batch * depth); H2D(ctx, dbits, path_bits, 4ull * batch); H2D(ctx, drs, rs, 64ull * batch);
+    OG_TRY(prove_withdraw_dev(ctx, pk, dn, dsx, dr, dsib, dbits, batch, drs, dpr, public_out ? dpub : nullptr));
+    D2H(ctx, proofs, dpr, 256ull * batch);
+    if (public_out) D2H(ctx, public_out, dpub, 32ull * batch * n_pub);
+    return check_flag(ctx);
+}
+
+int32_t og_groth16_h_evals(og_ctx* ctx, const og_pk* pk, const uint8_t* witness, uint8_t* out) {
+    if (!ctx || !pk || !witness || !out) return OG_E_INVALID;
+    uint32_t nv, log_m; pk_info(pk, &nv, nullptr, &log_m, nullptr);
+    OG_SLOT(ctx, dw, uint8_t, S_IO_A, 32ull * nv);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_B, 32ull << log_m);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, dw, witness, 32ull * nv);
+    OG_TRY(h_evals_dev(ctx, pk, dw, dout));
+    D2H(ctx, out, dout, 32ull << log_m);
+    return check_flag(ctx);
+}
+
+int32_t og_groth16_verify(const uint8_t* vk, uint64_t vk_len, const uint8_t* public_inputs, uint32_t n_pub, const uint8_t* proof256) {
+    if (!vk || !proof256 || (n_pub && !public_inputs)) return OG_E_INVALID;
+    return groth16_verify_host(vk, vk_len, public_inputs, n_pub, proof256);
+}
+
+}  // extern "C"

@@ -1,0 +1,523 @@
+// owshen_b200/csrc/msm.cu -- bucket-method (Pippenger) multi-scalar multiplication on BN254 G1/G2
+// for sm_100a.  BASELINE configs 3 and 5 and the inner engine of the batched Groth16 prover.
+//
+// No counterpart in the reference.  Pipeline:
+//   1. k_digits<false>   signed c-bit digits of every scalar, histogram of (group, bucket) keys
+//   2. k_scan            exclusive prefix sum of the histogram
+//   3. k_digits<true>    counting-sort scatter of (point index, sign) entries  -> coalesced bucket lists
+//   4. k_bucket_acc      one thread per bucket: XYZZ += affine point (8M+2S), accumulator in registers
+//      k_bucket_heavy    buckets above a cap get a whole CTA (witness-like scalars: 0/1 pile-ups)
+//   5. k_reduce_level    sum_b (b+1) B_b by 32-way running sums, log_32(nb) levels
+//   6. k_group_total / k_horner
+// All arithmetic is 8x32-bit Montgomery limbs in registers (fp.cuh); the kernels are bound by the
+// integer multiply-add pipe, not HBM: a G1 mixed add moves 64 B + 4 B and costs ~3.5k instructions.
+#include "msm.cuh"
+// Compiled twice: -DOG_MSM_G1 (G1 instantiations + the curve-independent sort) and -DOG_MSM_G2.
+#if !defined(OG_MSM_G1) && !defined(OG_MSM_G2)
+#error "compile msm.cu with -DOG_MSM_G1 or -DOG_MSM_G2"
+#endif
+
+namespace og {
+
+// ---- boundary conversions ---------------------------------------------------------------------------
+template <class F> struct FieldIO;
+template <> struct FieldIO<Fq> {
+    static constexpr int BYTES = 32;
+    static __device__ __forceinline__ Fq load(const uint8_t* p, int* flag) { return load_canonical<Fq>(p, flag); }
+    static __device__ __forceinline__ void store(uint8_t* p, const Fq& v) { store_canonical(p, v); }
+};
+template <> struct FieldIO<Fq2> {
+    static constexpr int BYTES = 64;
+    static __device__ __forceinline__ Fq2 load(const uint8_t* p, int* flag) {
+        return Fq2{load_canonical<Fq>(p, flag), load_canonical<Fq>(p + 32, flag)};
+    }
+    static __device__ __forceinline__ void store(uint8_t* p, const Fq2& v) { store_canonical(p, v.c0); store_canonical(p + 32, v.c1); }
+};
+
+template <class F>
+__global__ void __launch_bounds__(128) k_points_to_mont(const uint8_t* __restrict__ in, uint64_t n, Affine<F>* __restrict__ out, int* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int B = FieldIO<F>::BYTES;
+    const uint8_t* p = in + 2 * B * i;
+    out[i] = Affine<F>{FieldIO<F>::load(p, flag), FieldIO<F>::load(p + B, flag)};   // all-zero stays (0,0) = infinity
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_points_from_mont(const Affine<F>* __restrict__ in, uint64_t n, uint8_t* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int B = FieldIO<F>::BYTES;
+    Affine<F> p = in[i];
+    FieldIO<F>::store(out + 2 * B * i, p.x);
+    FieldIO<F>::store(out + 2 * B * i + B, p.y);
+}
+
+#ifdef OG_MSM_G1
+int32_t g1_bytes_to_mont(og_ctx* ctx, const uint8_t* d_in, uint64_t n, G1Affine* d_out) {
+    if (n) OG_LAUNCH(ctx, k_points_to_mont<Fq>, (unsigned)((n + 127) / 128), 128, 0, d_in, n, d_out, ctx->d_flag);
+    return OG_OK;
+}
+#endif  // OG_MSM_G1
+
+#ifdef OG_MSM_G2
+int32_t g2_bytes_to_mont(og_ctx* ctx, const uint8_t* d_in, uint64_t n, G2Affine* d_out) {
+    if (n) OG_LAUNCH(ctx, k_points_to_mont<Fq2>, (unsigned)((n + 127) / 128), 128, 0, d_in, n, d_out, ctx->d_flag);
+    return OG_OK;
+}
+#endif  // OG_MSM_G2
+
+#ifdef OG_MSM_G1
+int32_t g1_mont_to_bytes(og_ctx* ctx, const G1Affine* d_in, uint64_t n, uint8_t* d_out) {
+    if (n) OG_LAUNCH(ctx, k_points_from_mont<Fq>, (unsigned)((n + 127) / 128), 128, 0, d_in, n, d_out);
+    return OG_OK;
+}
+#endif  // OG_MSM_G1
+
+#ifdef OG_MSM_G2
+int32_t g2_mont_to_bytes(og_ctx* ctx, const G2Affine* d_in, uint64_t n, uint8_t* d_out) {
+    if (n) OG_LAUNCH(ctx, k_points_from_mont<Fq2>, (unsigned)((n + 127) / 128), 128, 0, d_in, n, d_out);
+    return OG_OK;
+}
+#endif  // OG_MSM_G2
+
+
+#ifdef OG_MSM_G1
+// ---- 1/3: digits -> histogram / scatter ---------------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t prob = blockIdx.y;
+    if (i >= P.n) return;
+    const uint32_t* sp = P.scalars + ((uint64_t)prob * P.scalar_stride + i) * 8;
+    uint32_t s[9];
+    if (P.montgomery) {
+        Fr v;
+#pragma unroll
+        for (int j = 0; j < 8; j++) v.l[j] = sp[j];
+        v.to_canonical(s);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) s[j] = sp[j];
+        if (!Fr::canonical_lt_mod(s)) { atomicOr(flag, 1); return; }
+    }
+    s[8] = 0;
+    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
+    const uint32_t c = P.c, half = 1u << (c - 1), mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < P.n_windows; w++) {
+        uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
+        uint64_t two = ((uint64_t)s[word + 1] << 32) | s[word];     // word <= 7 because n_windows*c <= 255 + c
+        uint32_t v = ((uint32_t)(two >> sh) & mask) + carry;
+        uint32_t neg = v > half;
+        uint32_t mag = neg ? (1u << c) - v : v;
+        carry = neg;
+        if (mag == 0) continue;
+        uint32_t key = (prob * P.key_stride_problem + w * P.key_stride_window) * P.nb + (mag - 1);
+        if (!SCATTER) {
+            atomicAdd(&counts[key], 1u);
+        } else {
+            uint32_t pos = offsets[key] + atomicAdd(&cursor[key], 1u);
+            sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
+        }
+    }
+}
+
+// ---- 2: exclusive scan (one CTA; n <= a few million keys) ------------------------------------------------
+__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t part[1024];
+    uint32_t t = threadIdx.x;
+    uint32_t chunk = (n + 1023) / 1024;
+    uint32_t lo = min(n, t * chunk), hi = min(n, lo + chunk);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += counts[i];
+    part[t] = s;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {          // Hillis-Steele inclusive scan
+        uint32_t v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = t ? part[t - 1] : 0;
+    for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
+    if (t == 1023) offsets[n] = part[1023];
+}
+
+int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uint32_t* d_counts, uint32_t* d_offsets,
+                        uint32_t* d_cursor, uint32_t* d_sorted) {
+    OG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)n_keys, ctx->stream));
+    OG_CUDA(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t) * (size_t)n_keys, ctx->stream));
+    if (plan.n == 0 || plan.n_problems == 0) {
+        OG_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * ((size_t)n_keys + 1), ctx->stream));
+        return OG_OK;
+    }
+    dim3 grid((unsigned)((plan.n + 255) / 256), plan.n_problems);
+    OG_LAUNCH(ctx, k_digits<false>, grid, 256, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
+    OG_LAUNCH(ctx, k_scan, 1, 1024, 0, d_counts, n_keys, d_offsets);
+    OG_LAUNCH(ctx, k_digits<true>, grid, 256, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
+    return OG_OK;
+}
+#endif  // OG_MSM_G1
+
+
+// ---- 4: bucket accumulation ----------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ Affine<F> fetch_point(const Affine<F>* __restrict__ table, uint32_t e) {
+    Affine<F> p = table[e >> 1];
+    if (e & 1) p.y = p.y.neg();
+    return p;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_bucket_acc(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
+                                                    const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                                    uint32_t n_keys, uint32_t cap, XYZZ<F>* __restrict__ buckets,
+                                                    uint32_t* __restrict__ heavy) {
+    uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    uint32_t cnt = counts[key], off = offsets[key];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (cnt > cap) {                               // left to k_bucket_heavy
+        uint32_t slot = atomicAdd(heavy, 1u);
+        heavy[1 + slot] = key;
+        buckets[key] = acc;
+        return;
+    }
+    if (cnt) {
+        Affine<F> nxt = fetch_point(table, sorted[off]);
+        for (uint32_t k = 0; k < cnt; k++) {
+            Affine<F> cur = nxt;
+            if (k + 1 < cnt) nxt = fetch_point(table, sorted[off + k + 1]);   // overlap the gather with the add
+            acc.madd(cur);
+        }
+    }
+    buckets[key] = acc;
+}
+
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_bucket_heavy(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
+                                                          const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                                          XYZZ<F>* __restrict__ buckets, const uint32_t* __restrict__ heavy) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    uint32_t n_heavy = heavy[0];
+    for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        uint32_t key = heavy[1 + h];
+        uint32_t cnt = counts[key], off = offsets[key];
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = threadIdx.x; k < cnt; k += THREADS) { Affine<F> q = fetch_point(table, sorted[off + k]); xyzz_madd_ni(&acc, &q); }
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int s = THREADS / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) xyzz_add_ni(&sh[threadIdx.x], &sh[threadIdx.x + s]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) buckets[key] = sh[0];
+        __syncthreads();
+    }
+}
+
+// ---- 5: weighted reduction, 32 children per parent -------------------------------------------------------
+// Element e of a level carries S_e (plain sum of the buckets under e) and U_e (their 0-based weighted sum
+// relative to e's first bucket).  Merging children c_0..c_k, each covering 2^w_log2 buckets:
+//   S_p = sum S_c;   U_p = sum U_c + 2^w_log2 * sum_c idx(c) * S_c   (running-sum trick for the last term).
+template <class F>
+__global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
+                                                     uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
+                                                     XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ U_out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups * n_out) return;
+    uint32_t g = t / n_out, p = t % n_out;
+    const XYZZ<F>* S = S_in + (size_t)g * n_in;
+    const XYZZ<F>* U = U_in ? U_in + (size_t)g * n_in : nullptr;
+    uint32_t lo = p * 32, hi = min(n_in, lo + 32);
+    XYZZ<F> R = XYZZ<F>::inf(), T = XYZZ<F>::inf(), Us = XYZZ<F>::inf();
+    for (uint32_t i = hi - 1; i > lo; i--) {
+        xyzz_add_ni(&R, &S[i]);
+        xyzz_add_ni(&T, &R);
+        if (U) xyzz_add_ni(&Us, &U[i]);
+    }
+    xyzz_add_ni(&R, &S[lo]);
+    if (U) xyzz_add_ni(&Us, &U[lo]);
+    for (uint32_t k = 0; k < w_log2; k++) xyzz_dbl_ni(&T);
+    xyzz_add_ni(&Us, &T);
+    S_out[(size_t)g * n_out + p] = R;
+    U_out[(size_t)g * n_out + p] = Us;
+}
+
+// total_g = U_g + S_g   (weights are b+1)
+template <class F>
+__global__ void __launch_bounds__(64) k_group_total(const XYZZ<F>* __restrict__ S, const XYZZ<F>* __restrict__ U, uint32_t n_groups,
+                                                    XYZZ<F>* __restrict__ out) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    XYZZ<F> a = U[g];
+    xyzz_add_ni(&a, &S[g]);
+    out[g] = a;
+}
+
+template <class F>
+static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
+                           const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, XYZZ<F>* d_buckets, XYZZ<F>* d_lvl,
+                           uint32_t* d_heavy, XYZZ<F>* d_totals) {
+    uint32_t n_keys = n_groups * nb;
+    constexpr int HT = sizeof(F) == 32 ? 256 : 128;
+    OG_CUDA(ctx, cudaMemsetAsync(d_heavy, 0, sizeof(uint32_t), ctx->stream));
+    // cap: a bucket that would keep one thread busy far longer than its warp-mates goes to a CTA
+    uint32_t cap = 4096;
+    OG_LAUNCH(ctx, k_bucket_acc<F>, (n_keys + 127) / 128, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy);
+    auto k_heavy = k_bucket_heavy<F, HT>;
+    OG_LAUNCH(ctx, k_heavy, ctx->sm_count, HT, HT * sizeof(XYZZ<F>), d_table, d_sorted, d_offsets, d_counts, d_buckets, d_heavy);
+    // reduction levels
+    size_t lvl_stride = (size_t)n_groups * ((nb + 31) / 32) + 16;
+    XYZZ<F>* bufS[2] = {d_lvl, d_lvl + lvl_stride};
+    XYZZ<F>* bufU[2] = {d_lvl + 2 * lvl_stride, d_lvl + 3 * lvl_stride};
+    const XYZZ<F>* S_in = d_buckets;
+    const XYZZ<F>* U_in = nullptr;
+    uint32_t n_in = nb, w_log2 = 0;
+    int pp = 0;
+    do {
+        uint32_t n_out = (n_in + 31) / 32;
+        uint32_t threads = n_groups * n_out;
+        OG_LAUNCH(ctx, k_reduce_level<F>, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]);
+        S_in = bufS[pp]; U_in = bufU[pp];
+        pp ^= 1;
+        n_in = n_out;
+        w_log2 += 5;
+    } while (n_in > 1);
+    OG_LAUNCH(ctx, k_group_total<F>, (n_groups + 63) / 64, 64, 0, S_in, U_in, n_groups, d_totals);
+    return OG_OK;
+}
+
+#ifdef OG_MSM_G1
+int32_t msm_buckets_g1(og_ctx* ctx, const G1Affine* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
+                       const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, G1XYZZ* d_buckets, G1XYZZ* d_lvl,
+                       uint32_t* d_heavy, G1XYZZ* d_totals) {
+    return msm_buckets<Fq>(ctx, d_table, d_sorted, d_offsets, d_counts, n_groups, nb, d_buckets, d_lvl, d_heavy, d_totals);
+}
+#endif  // OG_MSM_G1
+
+#ifdef OG_MSM_G2
+int32_t msm_buckets_g2(og_ctx* ctx, const G2Affine* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
+                       const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, G2XYZZ* d_buckets, G2XYZZ* d_lvl,
+                       uint32_t* d_heavy, G2XYZZ* d_totals) {
+    return msm_buckets<Fq2>(ctx, d_table, d_sorted, d_offsets, d_counts, n_groups, nb, d_buckets, d_lvl, d_heavy, d_totals);
+}
+#endif  // OG_MSM_G2
+
+
+// ---- 6: one-shot MSM = Horner over the window totals ------------------------------------------------------
+template <class F>
+__global__ void k_horner(const XYZZ<F>* __restrict__ totals, uint32_t n_windows, uint32_t c, uint8_t* __restrict__ out) {
+    if (blockIdx.x || threadIdx.x) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (int w = (int)n_windows - 1; w >= 0; w--) {
+        for (uint32_t k = 0; k < c; k++) xyzz_dbl_ni(&acc);
+        xyzz_add_ni(&acc, &totals[w]);
+    }
+    Affine<F> a;
+    xyzz_to_affine_ni(&a, &acc);
+    constexpr int B = FieldIO<F>::BYTES;
+    FieldIO<F>::store(out, a.x);
+    FieldIO<F>::store(out + B, a.y);
+}
+
+static uint32_t pick_window(uint64_t n) {
+    uint32_t lg = 0;
+    while ((1ull << (lg + 1)) <= n) lg++;
+    int c = (int)lg - 3;
+    if (c < 2) c = 2;
+    if (c > 16) c = 16;
+    return (uint32_t)c;
+}
+
+template <class F>
+static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out) {
+    constexpr int PB = 2 * FieldIO<F>::BYTES;
+    if (n >= (1ull << 28)) return OG_E_INVALID;
+    if (!aligned32(d_points) || !aligned32(d_scalars)) return OG_E_INVALID;
+    if (n == 0) { OG_CUDA(ctx, cudaMemsetAsync(d_out, 0, PB, ctx->stream)); return OG_OK; }
+    uint32_t c = pick_window(n), W = msm_windows(c), nb = 1u << (c - 1);
+    uint32_t n_keys = W * nb;
+    OG_SLOT(ctx, pts, Affine<F>, S_MSM_POINTS, sizeof(Affine<F>) * n);
+    OG_SLOT(ctx, counts, uint32_t, S_MSM_COUNTS, 4 * (size_t)n_keys);
+    OG_SLOT(ctx, offsets, uint32_t, S_MSM_OFFSETS, 4 * ((size_t)n_keys + 1));
+    OG_SLOT(ctx, cursor, uint32_t, S_MSM_CURSOR, 4 * (size_t)n_keys);
+    OG_SLOT(ctx, sorted, uint32_t, S_MSM_SORTED, 4 * (size_t)n * W);
+    OG_SLOT(ctx, buckets, XYZZ<F>, S_MSM_BUCKETS, sizeof(XYZZ<F>) * (size_t)n_keys);
+    OG_SLOT(ctx, lvl, XYZZ<F>, S_MSM_SEG, sizeof(XYZZ<F>) * 4 * ((size_t)W * ((nb + 31) / 32) + 16));
+    OG_SLOT(ctx, heavy, uint32_t, S_MSM_HEAVY, 4 * ((size_t)n_keys + 1));
+    OG_SLOT(ctx, totals, XYZZ<F>, S_MSM_OUT, sizeof(XYZZ<F>) * W);
+    OG_LAUNCH(ctx, k_points_to_mont<F>, (unsigned)((n + 127) / 128), 128, 0, d_points, n, pts, ctx->d_flag);
+    DigitPlan plan;
+    plan.scalars = reinterpret_cast<const uint32_t*>(d_scalars);
+    plan.n = n; plan.scalar_stride = 0; plan.n_problems = 1;
+    plan.c = c; plan.n_windows = W; plan.nb = nb;
+    plan.key_stride_problem = 0; plan.key_stride_window = 1; plan.tidx_window_stride = 0;
+    plan.montgomery = 0;
+    OG_TRY(msm_sort_digits(ctx, plan, n_keys, counts, offsets, cursor, sorted));
+    OG_TRY((msm_buckets<F>(ctx, pts, sorted, offsets, counts, W, nb, buckets, lvl, heavy, totals)));
+    OG_LAUNCH(ctx, k_horner<F>, 1, 32, 0, totals, W, c, d_out);
+    return OG_OK;
+}
+
+#ifdef OG_MSM_G1
+int32_t msm_g1_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out64) {
+    return msm_dev<Fq>(ctx, d_points, d_scalars, n, d_out64);
+}
+#endif  // OG_MSM_G1
+
+#ifdef OG_MSM_G2
+int32_t msm_g2_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out128) {
+    return msm_dev<Fq2>(ctx, d_points, d_scalars, n, d_out128);
+}
+#endif  // OG_MSM_G2
+
+
+// ---- plain sum of affine points (post all-gather combine in the sharded MSM) ------------------------------------
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_sum_points(const uint8_t* __restrict__ pts, uint64_t n, uint8_t* __restrict__ out, int* flag) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
+    constexpr int B = FieldIO<F>::BYTES;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint64_t i = threadIdx.x; i < n; i += THREADS) {
+        const uint8_t* p = pts + 2 * B * i;
+        Affine<F> q{FieldIO<F>::load(p, flag), FieldIO<F>::load(p + B, flag)};
+        xyzz_madd_ni(&acc, &q);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) xyzz_add_ni(&sh[threadIdx.x], &sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        Affine<F> a;
+        xyzz_to_affine_ni(&a, &sh[0]);
+        FieldIO<F>::store(out, a.x);
+        FieldIO<F>::store(out + B, a.y);
+    }
+}
+#ifdef OG_MSM_G1
+int32_t sum_g1_dev(og_ctx* ctx, const uint8_t* d_points, uint64_t n, uint8_t* d_out64) {
+    auto k = k_sum_points<Fq, 128>;
+    OG_LAUNCH(ctx, k, 1, 128, 128 * sizeof(G1XYZZ), d_points, n, d_out64, ctx->d_flag);
+    return OG_OK;
+}
+#endif  // OG_MSM_G1
+
+#ifdef OG_MSM_G2
+int32_t sum_g2_dev(og_ctx* ctx, const uint8_t* d_points, uint64_t n, uint8_t* d_out128) {
+    auto k = k_sum_points<Fq2, 128>;
+    OG_LAUNCH(ctx, k, 1, 128, 128 * sizeof(G2XYZZ), d_points, n, d_out128, ctx->d_flag);
+    return OG_OK;
+}
+#endif  // OG_MSM_G2
+
+
+// ---- fixed-base window tables ------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(64) k_build_table(Affine<F>* __restrict__ table, uint32_t n, uint32_t c, uint32_t n_windows) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = table[i];
+    for (uint32_t w = 1; w < n_windows; w++) {
+        XYZZ<F> x = XYZZ<F>::from_affine(p);
+        for (uint32_t k = 0; k < c; k++) xyzz_dbl_ni(&x);
+        xyzz_to_affine_ni(&p, &x);
+        table[(size_t)w * n + i] = p;
+    }
+}
+#ifdef OG_MSM_G1
+int32_t msm_build_table_g1(og_ctx* ctx, G1Affine* d_table, uint32_t n, uint32_t c, uint32_t n_windows) {
+    if (n) OG_LAUNCH(ctx, k_build_table<Fq>, (n + 63) / 64, 64, 0, d_table, n, c, n_windows);
+    return OG_OK;
+}
+#endif  // OG_MSM_G1
+
+#ifdef OG_MSM_G2
+int32_t msm_build_table_g2(og_ctx* ctx, G2Affine* d_table, uint32_t n, uint32_t c, uint32_t n_windows) {
+    if (n) OG_LAUNCH(ctx, k_build_table<Fq2>, (n + 63) / 64, 64, 0, d_table, n, c, n_windows);
+    return OG_OK;
+}
+#endif  // OG_MSM_G2
+
+
+// ---- fixed-base multiplication by the generators (development setup only) ------------------------------------------
+// gen_table[w * 255 + d - 1] = d * 2^(8w) * G,  w < 32, d in 1..255
+template <class F>
+__global__ void __launch_bounds__(32) k_gen_table(Affine<F> gen, Affine<F>* __restrict__ tab) {
+    uint32_t w = threadIdx.x;
+    if (w >= 32) return;
+    XYZZ<F> x = XYZZ<F>::from_affine(gen);
+    for (uint32_t k = 0; k < 8 * w; k++) xyzz_dbl_ni(&x);
+    Affine<F> base, t;
+    xyzz_to_affine_ni(&base, &x);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t d = 1; d < 256; d++) {
+        xyzz_madd_ni(&acc, &base);
+        xyzz_to_affine_ni(&t, &acc);
+        tab[w * 255 + d - 1] = t;
+    }
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_fixed_mul(const Affine<F>* __restrict__ tab, const uint8_t* __restrict__ scalars, uint64_t n,
+                                                   Affine<F>* __restrict__ out, int* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(scalars + 32 * i);
+    uint32_t s[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s[j] = sp[j];
+    if (!Fr::canonical_lt_mod(s)) { atomicOr(flag, 1); out[i] = Affine<F>::inf(); return; }
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t w = 0; w < 32; w++) {
+        uint32_t d = (s[w >> 2] >> ((w & 3) * 8)) & 255;
+        if (d) xyzz_madd_ni(&acc, &tab[w * 255 + d - 1]);
+    }
+    Affine<F> r;
+    xyzz_to_affine_ni(&r, &acc);
+    out[i] = r;
+}
+
+#ifdef OG_MSM_G2
+static const uint32_t G2_GEN_X0[8] = {0xd992f6edu, 0x46debd5cu, 0xf75edaddu, 0x674322d4u, 0x5e5c4479u, 0x426a0066u, 0x121f1e76u, 0x1800deefu};
+static const uint32_t G2_GEN_X1[8] = {0xaef312c2u, 0x97e485b7u, 0x35a9e712u, 0xf1aa4933u, 0x31fb5d25u, 0x7260bfb7u, 0x920d483au, 0x198e9393u};
+static const uint32_t G2_GEN_Y0[8] = {0x66fa7daau, 0x4ce6cc01u, 0x0c43d37bu, 0xe3d1e769u, 0x8dcb408fu, 0x4aab7180u, 0xdb8c6debu, 0x12c85ea5u};
+static const uint32_t G2_GEN_Y1[8] = {0xd122975bu, 0x55acdadcu, 0x70b38ef3u, 0xbc4b3133u, 0x690c3395u, 0xec9e99adu, 0x585ff075u, 0x090689d0u};
+#endif  // OG_MSM_G2
+
+
+#ifdef OG_MSM_G1
+int32_t fixed_base_mul_g1(og_ctx* ctx, const uint8_t* d_scalars, uint64_t n, G1Affine* d_out) {
+    if (!ctx->g1_fixed) {
+        G1Affine* tab;
+        OG_CUDA(ctx, cudaMalloc(&tab, sizeof(G1Affine) * 32 * 255));
+        G1Affine gen{Fq::from_u32(1), Fq::from_u32(2)};
+        OG_LAUNCH(ctx, k_gen_table<Fq>, 1, 32, 0, gen, tab);
+        ctx->g1_fixed = tab;
+    }
+    if (n) OG_LAUNCH(ctx, k_fixed_mul<Fq>, (unsigned)((n + 127) / 128), 128, 0, (const G1Affine*)ctx->g1_fixed, d_scalars, n, d_out, ctx->d_flag);
+    return OG_OK;
+}
+#endif  // OG_MSM_G1
+
+#ifdef OG_MSM_G2
+int32_t fixed_base_mul_g2(og_ctx* ctx, const uint8_t* d_scalars, uint64_t n, G2Affine* d_out) {
+    if (!ctx->g2_fixed) {
+        G2Affine* tab;
+        OG_CUDA(ctx, cudaMalloc(&tab, sizeof(G2Affine) * 32 * 255));
+        G2Affine gen{Fq2{Fq::from_canonical(G2_GEN_X0), Fq::from_canonical(G2_GEN_X1)},
+                     Fq2{Fq::from_canonical(G2_GEN_Y0), Fq::from_canonical(G2_GEN_Y1)}};
+        OG_LAUNCH(ctx, k_gen_table<Fq2>, 1, 32, 0, gen, tab);
+        ctx->g2_fixed = tab;
+    }
+    if (n) OG_LAUNCH(ctx, k_fixed_mul<Fq2>, (unsigned)((n + 127) / 128), 128, 0, (const G2Affine*)ctx->g2_fixed, d_scalars, n, d_out, ctx->d_flag);
+    return OG_OK;
+}
+#endif  // OG_MSM_G2
+
+
+}  // namespace og

@@ -1,0 +1,182 @@
+// owshen_b200/csrc/ntt.cu -- batched radix-2 NTT over BN254 Fr for sm_100a.
+//
+// No counterpart in the reference; convention follows its field generator 7
+// (/root/reference/src/blockchain/tx/owshen_airdrop/babyjubjub/mod.rs:9): omega_n = 7^((r-1)/n),
+// forward out[k] = sum_j in[j] omega^(jk), natural order in and out; "coset" evaluates on g*omega^k
+// with g = omega_{2n}.
+//
+// Decimation-in-time with the stages grouped into passes; a pass stages a tile of <= 1024
+// coefficients (32 KB) in shared memory and runs up to 10 butterfly levels there, so a 2^15
+// transform (the Groth16 domain of the withdraw circuit) is two global passes.  Pass 1 gathers its
+// tile in bit-reversed order (32 B elements = one DRAM sector each, so the gather wastes no
+// bandwidth) and fuses the coset scaling; the last pass fuses 1/n and the inverse coset shift.
+// Later passes own 2^K strided rows x 8 consecutive columns so that global accesses are 256 B runs.
+// One table per size serves everything: T2[j] = omega_{2n}^j (j < n): coset factors are T2[j],
+// stage twiddles are omega_n^e = T2[2e], inverses are -T2[n - j].
+#include "ntt.cuh"
+
+namespace og {
+
+struct NttTables {
+    uint32_t log_n;
+    Fr* d_t2;      // omega_{2n}^j, j < n, Montgomery form
+    Fr n_inv;      // 1/n, Montgomery form
+};
+
+__global__ void __launch_bounds__(256) k_ntt_table(Fr g, uint64_t n, Fr* __restrict__ t2) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Fr acc = Fr::one(), base = g;
+    for (uint64_t e = j; e; e >>= 1) {
+        if (e & 1) acc = acc * base;
+        base = base.sqr();
+    }
+    t2[j] = acc;
+}
+
+// omega_{2n}^(+-j), 0 <= j < n
+__device__ __forceinline__ Fr tw2(const Fr* __restrict__ t2, uint32_t n, uint32_t j, bool inverse) {
+    if (!inverse || j == 0) return t2[j];
+    return t2[n - j].neg();
+}
+
+struct PassPlan {
+    uint32_t log_n;
+    uint32_t s0;        // first (1-based) DIT stage of this pass
+    uint32_t K;         // stages in this pass
+    uint32_t L;         // log2 of consecutive columns per tile (0 in the first pass)
+    uint32_t first, last, inverse, coset;
+};
+
+__device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return __brev(x) >> (32 - bits); }
+
+__global__ void __launch_bounds__(512) k_ntt_pass(PassPlan P, const Fr* __restrict__ in, Fr* __restrict__ out,
+                                                  const Fr* __restrict__ t2, Fr n_inv) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    Fr* sm = reinterpret_cast<Fr*>(smem_raw);
+    const uint32_t n = 1u << P.log_n;
+    const uint32_t B0 = P.s0 - 1;                     // index bits below the ones this pass transforms
+    const uint32_t tile = 1u << (P.K + P.L);
+    const uint32_t t = blockIdx.x;
+    const uint32_t mid = t & ((1u << (B0 - P.L)) - 1), top = t >> (B0 - P.L);
+    const uint32_t base = (top << (B0 + P.K)) | (mid << P.L);
+    const Fr* src = in + (size_t)blockIdx.y * n;
+    Fr* dst = out + (size_t)blockIdx.y * n;
+    const uint32_t lmask = (1u << P.L) - 1;
+
+    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
+        uint32_t lo = e & lmask, k = e >> P.L;
+        uint32_t i = base | (k << B0) | lo;
+        Fr v;
+        if (P.first) {
+            uint32_t j = bitrev(i, P.log_n);
+            v = src[j];
+            if (P.coset && !P.inverse) v = v * t2[j];
+        } else {
+            v = src[i];
+        }
+        sm[e] = v;
+    }
+    __syncthreads();
+
+    for (uint32_t q = 1; q <= P.K; q++) {
+        const uint32_t s = P.s0 + q - 1;               // global stage: block size 2^s
+        for (uint32_t b = threadIdx.x; b < (tile >> 1); b += blockDim.x) {
+            uint32_t lo = b & lmask, kb = b >> P.L;
+            uint32_t klow = kb & ((1u << (q - 1)) - 1);
+            uint32_t k0 = ((kb >> (q - 1)) << q) | klow;
+            uint32_t e0 = (k0 << P.L) | lo, e1 = e0 + ((1u << (q - 1)) << P.L);
+            uint32_t j = (klow << B0) | (mid << P.L) | lo;          // index within the half-block, < 2^(s-1)
+            Fr w = tw2(t2, n, j << (P.log_n + 1 - s), P.inverse);   // omega_{2^s}^j = omega_{2n}^(j * 2n/2^s)
+            Fr u = sm[e0];
+            Fr v = sm[e1] * w;
+            sm[e0] = u + v;
+            sm[e1] = u - v;
+        }
+        __syncthreads();
+    }
+
+    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
+        uint32_t lo = e & lmask, k = e >> P.L;
+        uint32_t i = base | (k << B0) | lo;
+        Fr v = sm[e];
+        if (P.last && P.inverse) {
+            v = v * n_inv;
+            if (P.coset) v = v * tw2(t2, n, i, true);
+        }
+        dst[i] = v;
+    }
+}
+
+static int32_t get_tables(og_ctx* ctx, uint32_t log_n, NttTables** out) {
+    if (log_n > 27) return OG_E_INVALID;
+    if (!ctx->ntt[log_n]) {
+        NttTables* T = new NttTables();
+        T->log_n = log_n;
+        uint64_t n = 1ull << log_n;
+        OG_CUDA(ctx, cudaMalloc(&T->d_t2, sizeof(Fr) * n));
+        // g = 7^((r-1) >> (log_n+1)) on the host
+        uint32_t e[8];
+        for (int i = 0; i < 8; i++) e[i] = FrParams::mod(i);
+        e[0] -= 1;
+        for (uint32_t k = 0; k < log_n + 1; k++) {
+            for (int i = 0; i < 7; i++) e[i] = (e[i] >> 1) | (e[i + 1] << 31);
+            e[7] >>= 1;
+        }
+        Fr g = Fr::from_u32(7).pow(e);
+        OG_LAUNCH(ctx, k_ntt_table, (unsigned)((n + 255) / 256), 256, 0, g, n, T->d_t2);
+        uint32_t nn[8] = {0};
+        nn[log_n >> 5] = 1u << (log_n & 31);
+        T->n_inv = Fr::from_canonical(nn).inv();
+        ctx->ntt[log_n] = T;
+    }
+    *out = ctx->ntt[log_n];
+    return OG_OK;
+}
+
+void ntt_free_tables(og_ctx* ctx) {
+    for (int i = 0; i < 32; i++)
+        if (ctx->ntt[i]) { cudaFree(ctx->ntt[i]->d_t2); delete ctx->ntt[i]; ctx->ntt[i] = nullptr; }
+}
+
+// In-place on `data` (Montgomery form); `tmp` must hold batch * n elements when log_n > 10.
+int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t batch, int inverse, int coset) {
+    if (batch == 0) return OG_OK;
+    NttTables* T;
+    OG_TRY(get_tables(ctx, log_n, &T));
+    if (log_n == 0) {
+        return OG_OK;   // size-1 transform: identity (coset factor g^0 = 1, 1/n = 1)
+    }
+    // plan the passes
+    PassPlan plans[8];
+    int np = 0;
+    uint32_t done = 0;
+    while (done < log_n) {
+        PassPlan p;
+        p.log_n = log_n; p.s0 = done + 1; p.inverse = inverse; p.coset = coset; p.first = (done == 0); p.last = 0;
+        if (done == 0) { p.K = log_n < 10 ? log_n : 10; p.L = 0; }
+        else {
+            p.L = done < 3 ? done : 3;
+            uint32_t rest = log_n - done, maxk = 10 - p.L;
+            // balance the remaining stages over the passes still needed
+            uint32_t passes = (rest + maxk - 1) / maxk;
+            p.K = (rest + passes - 1) / passes;
+        }
+        done += p.K;
+        plans[np++] = p;
+    }
+    plans[np - 1].last = 1;
+    for (int i = 0; i < np; i++) {
+        const PassPlan& p = plans[i];
+        const Fr* src = (i == 0) ? data : tmp;
+        Fr* dst = (i == np - 1) ? data : tmp;
+        if (np == 1) { src = data; dst = data; }
+        uint32_t tile = 1u << (p.K + p.L);
+        uint32_t threads = tile / 2 < 32 ? 32 : (tile / 2 > 512 ? 512 : tile / 2);
+        dim3 grid((1u << log_n) / tile, batch);
+        OG_LAUNCH(ctx, k_ntt_pass, grid, threads, tile * sizeof(Fr), p, src, dst, T->d_t2, T->n_inv);
+    }
+    return OG_OK;
+}
+
+}  // namespace og

@@ -1,0 +1,55 @@
+// tests/harness/host_harness.cpp -- compiles the product's limb algorithms (fp.cuh / ec.cuh) for the
+// HOST so tests can run the exact even/odd Montgomery rows and XYZZ formulas without a GPU and
+// compare them with the oracle.  Test-only; the product never proves on the host.
+#include "fp.cuh"
+#include "ec.cuh"
+#include <cstring>
+using namespace og;
+
+template <class F> static F load(const uint8_t* b) { uint32_t c[8]; memcpy(c, b, 32); return F::from_canonical(c); }
+template <class F> static void store(uint8_t* b, const F& v) { uint32_t c[8]; v.to_canonical(c); memcpy(b, c, 32); }
+static Fq2 load2(const uint8_t* b) { return Fq2{load<Fq>(b), load<Fq>(b + 32)}; }
+static void store2(uint8_t* b, const Fq2& v) { store(b, v.c0); store(b + 32, v.c1); }
+static G1Affine loadg1(const uint8_t* b) { return G1Affine{load<Fq>(b), load<Fq>(b + 32)}; }
+static void storeg1(uint8_t* b, const G1Affine& p) { store(b, p.x); store(b + 32, p.y); }
+static G2Affine loadg2(const uint8_t* b) { return G2Affine{load2(b), load2(b + 64)}; }
+static void storeg2(uint8_t* b, const G2Affine& p) { store2(b, p.x); store2(b + 64, p.y); }
+
+extern "C" {
+#define BINOP(name, F, expr) \
+    void name(const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t n) { \
+        for (uint64_t i = 0; i < n; i++) { F x = load<F>(a + 32 * i), y = load<F>(b + 32 * i); store(out + 32 * i, expr); } }
+BINOP(ht_fq_mul, Fq, x * y)
+BINOP(ht_fq_add, Fq, x + y)
+BINOP(ht_fq_sub, Fq, x - y)
+BINOP(ht_fr_mul, Fr, x * y)
+BINOP(ht_fr_add, Fr, x + y)
+BINOP(ht_fr_sub, Fr, x - y)
+void ht_fq_inv(const uint8_t* a, uint8_t* out, uint64_t n) { for (uint64_t i = 0; i < n; i++) store(out + 32 * i, load<Fq>(a + 32 * i).inv()); }
+void ht_fr_inv(const uint8_t* a, uint8_t* out, uint64_t n) { for (uint64_t i = 0; i < n; i++) store(out + 32 * i, load<Fr>(a + 32 * i).inv()); }
+void ht_fq2_mul(const uint8_t* a, const uint8_t* b, uint8_t* out) { store2(out, load2(a) * load2(b)); }
+void ht_fq2_sqr(const uint8_t* a, uint8_t* out) { store2(out, load2(a).sqr()); }
+void ht_fq2_inv(const uint8_t* a, uint8_t* out) { store2(out, load2(a).inv()); }
+
+void ht_g1_mul(const uint8_t* p, const uint8_t* k, uint8_t* out) { uint32_t s[8]; memcpy(s, k, 32); storeg1(out, G1XYZZ::mul(loadg1(p), s).to_affine()); }
+void ht_g2_mul(const uint8_t* p, const uint8_t* k, uint8_t* out) { uint32_t s[8]; memcpy(s, k, 32); storeg2(out, G2XYZZ::mul(loadg2(p), s).to_affine()); }
+// sum of n affine points, through madd (mode 0) or through XYZZ+XYZZ add of lifted points (mode 1)
+void ht_g1_sum(const uint8_t* pts, uint64_t n, int mode, uint8_t* out) {
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint64_t i = 0; i < n; i++) {
+        G1Affine q = loadg1(pts + 64 * i);
+        if (mode == 0) acc.madd(q);
+        else { G1XYZZ t = G1XYZZ::from_affine(q); t = t.dbl(); t.madd(q.neg()); acc.add(t); }  // 2q - q
+    }
+    storeg1(out, acc.to_affine());
+}
+void ht_g2_sum(const uint8_t* pts, uint64_t n, int mode, uint8_t* out) {
+    G2XYZZ acc = G2XYZZ::inf();
+    for (uint64_t i = 0; i < n; i++) {
+        G2Affine q = loadg2(pts + 128 * i);
+        if (mode == 0) acc.madd(q);
+        else { G2XYZZ t = G2XYZZ::from_affine(q); t = t.dbl(); t.madd(q.neg()); acc.add(t); }
+    }
+    storeg2(out, acc.to_affine());
+}
+}
