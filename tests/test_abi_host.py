@@ -1,0 +1,88 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol include/owshen_b200.h declares,
+refuses to run without a device (no CPU fallback), and its host-side logic (withdraw R1CS builder, MiMC7
+constant derivation, Groth16 verifier) agrees with the oracle."""
+import os
+import random
+import re
+
+import pytest
+
+import owshen_b200 as ob
+from owshen_b200 import api
+from oracle import bn254 as bn
+from oracle import cport, mimc7
+from oracle.withdraw_circuit import build_r1cs, witness
+from tests.helpers import vk_blob
+
+R = bn.R
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    hdr = open(os.path.join(ROOT, "include", "owshen_b200.h")).read()
+    declared = set(re.findall(r"\b(og_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "header parse failed"
+    L = ob.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/owshen_b200.h but not exported"
+    assert declared == set(api.ABI_SYMBOLS), declared ^ set(api.ABI_SYMBOLS)
+    assert L.og_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(ob.OwshenB200Error) as e:
+        ob.Context(0)
+    assert e.value.code == -3
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "owshen_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert '#include "../../oracle' not in src and "liboracle" not in src, f
+
+
+def test_mimc_constants_derived_by_the_product():
+    assert api.mimc7_constants() == mimc7.CONSTANTS
+
+
+@pytest.mark.parametrize("depth", [1, 2, 32])
+def test_withdraw_r1cs_matches_spec(depth):
+    cs = build_r1cs(depth)
+    info = api.r1cs_info(depth)
+    assert (info["n_constraints"], info["n_vars"], info["n_pub"]) == (cs.n_constraints, cs.n_vars, cs.n_pub)
+    for m in "ABC":
+        ptr, col, val = api.r1cs_export(depth, m)
+        eptr, ecol, eval_ = cs.csr(m)
+        assert ptr == eptr and col == ecol and val == eval_, m
+
+
+def test_host_verifier_accepts_oracle_proof_and_rejects_tampering():
+    rng = random.Random(9)
+    depth = 4
+    cs = build_r1cs(depth)
+    pkb, vkb = cport.setup_bytes(cs, *[rng.randrange(1, R) for _ in range(5)])
+    sib = [rng.randrange(R) for _ in range(depth)]
+    w = witness(11, 22, 33, sib, [1, 0, 1, 1])
+    pr = cport.Prover(cs, pkb)
+    proof = pr.prove(cport.frs(w), 5, 7)
+    vk = vk_blob(vkb)
+    pub = cport.frs(w[1:4])
+    assert ob.verify(vk, pub, proof)
+    bad = bytearray(pub); bad[0] ^= 1
+    assert not ob.verify(vk, bytes(bad), proof)
+    other = pr.prove(cport.frs(w), 6, 7)
+    assert ob.verify(vk, pub, other)
+    assert not ob.verify(vk, pub, proof[:64] + other[64:])
+    with pytest.raises(ob.OwshenB200Error):
+        ob.verify(vk, pub, b"\xff" * 256)          # non-canonical coordinates
+    with pytest.raises(ob.OwshenB200Error):
+        ob.verify(vk[:-1], pub, proof)
+    # a point that is on the curve but the proof is garbage -> False, not an exception
+    g1, g2 = bn.g1_to_bytes(bn.G1_GEN), bn.g2_to_bytes(bn.G2_GEN)
+    assert not ob.verify(vk, pub, g1 + g2 + g1)

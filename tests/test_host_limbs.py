@@ -1,0 +1,82 @@
+"""The product's limb algorithms (fp.cuh even/odd Montgomery rows, ec.cuh XYZZ formulas) compiled for
+the host with the PTX carry chain emulated, against the oracle.  This checks the algorithm the GPU
+runs, without a GPU; the -m gpu tests check the real PTX path."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import bn254 as bn
+from oracle import cport
+
+R, P = bn.R, bn.P
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def h():
+    so = os.path.join(ROOT, "tests", "harness", "libhost_harness.so")
+    src = os.path.join(ROOT, "tests", "harness", "host_harness.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + os.path.join(ROOT, "owshen_b200", "csrc"),
+                    "-o", so, src], check=True)
+    return C.CDLL(so)
+
+
+def _binop(h, name, a, b):
+    out = C.create_string_buffer(len(a))
+    getattr(h, name)(a, b, out, C.c_uint64(len(a) // 32))
+    return out.raw
+
+
+def test_field_limbs(h):
+    rng = random.Random(1)
+    for F, mod, pack in (("fq", P, cport.fqs), ("fr", R, cport.frs)):
+        xs = [rng.randrange(mod) for _ in range(3000)] + [0, 1, mod - 1, mod - 1, 2**253, mod - 2, 2**32 - 1]
+        ys = [rng.randrange(mod) for _ in range(3000)] + [mod - 1, mod - 1, mod - 1, 1, 2**253, mod - 2, 2**224]
+        assert cport.unfr(_binop(h, f"ht_{F}_mul", pack(xs), pack(ys))) == [a * b % mod for a, b in zip(xs, ys)]
+        assert cport.unfr(_binop(h, f"ht_{F}_add", pack(xs), pack(ys))) == [(a + b) % mod for a, b in zip(xs, ys)]
+        assert cport.unfr(_binop(h, f"ht_{F}_sub", pack(xs), pack(ys))) == [(a - b) % mod for a, b in zip(xs, ys)]
+        out = C.create_string_buffer(32 * 5)
+        getattr(h, f"ht_{F}_inv")(pack(xs[:5]), out, C.c_uint64(5))
+        assert cport.unfr(out.raw) == [pow(a, -1, mod) for a in xs[:5]]
+
+
+def test_fq2(h):
+    rng = random.Random(2)
+    a = (rng.randrange(P), rng.randrange(P)); b = (rng.randrange(P), rng.randrange(P))
+    o = C.create_string_buffer(64)
+    h.ht_fq2_mul(cport.fqs(a), cport.fqs(b), o); assert tuple(cport.unfr(o.raw)) == bn.f2_mul(a, b)
+    h.ht_fq2_sqr(cport.fqs(a), o); assert tuple(cport.unfr(o.raw)) == bn.f2_sqr(a)
+    h.ht_fq2_inv(cport.fqs(a), o); assert tuple(cport.unfr(o.raw)) == bn.f2_inv(a)
+
+
+def test_group_formulas_with_exceptional_cases(h):
+    rng = random.Random(3)
+    for k in [0, 1, 2, 3, R - 1, rng.randrange(R)]:
+        o = C.create_string_buffer(64); h.ht_g1_mul(bn.g1_to_bytes(bn.G1_GEN), bn.fr_to_bytes(k), o)
+        assert o.raw == bn.g1_to_bytes(bn.g1_mul(bn.G1_GEN, k))
+        o = C.create_string_buffer(128); h.ht_g2_mul(bn.g2_to_bytes(bn.G2_GEN), bn.fr_to_bytes(k), o)
+        assert o.raw == bn.g2_to_bytes(bn.g2_mul(bn.G2_GEN, k))
+    pts = [bn.g1_mul(bn.G1_GEN, rng.randrange(R)) for _ in range(6)]
+    pts = pts + [pts[0], None, bn.g1_neg(pts[1]), pts[2], pts[2]]       # P+P, infinity, P+(-P)
+    exp = None
+    for p in pts:
+        exp = bn.g1_add(exp, p)
+    for mode in (0, 1):
+        o = C.create_string_buffer(64)
+        h.ht_g1_sum(b"".join(map(bn.g1_to_bytes, pts)), C.c_uint64(len(pts)), mode, o)
+        assert o.raw == bn.g1_to_bytes(exp)
+    seq = [pts[0], pts[0], bn.g1_neg(bn.g1_mul(pts[0], 2))]
+    o = C.create_string_buffer(64); h.ht_g1_sum(b"".join(map(bn.g1_to_bytes, seq)), C.c_uint64(3), 0, o)
+    assert o.raw == bytes(64)
+    pts2 = [bn.g2_mul(bn.G2_GEN, rng.randrange(R)) for _ in range(3)]
+    pts2 = pts2 + [pts2[0], None, bn.g2_neg(pts2[1])]
+    exp = None
+    for p in pts2:
+        exp = bn.g2_add(exp, p)
+    for mode in (0, 1):
+        o = C.create_string_buffer(128)
+        h.ht_g2_sum(b"".join(map(bn.g2_to_bytes, pts2)), C.c_uint64(len(pts2)), mode, o)
+        assert o.raw == bn.g2_to_bytes(exp)
