@@ -59,6 +59,10 @@ int32_t og_timer_start(og_ctx* ctx);
 int32_t og_timer_stop(og_ctx* ctx, float* ms);
 /* number of this library's kernel launches enqueued on ctx since creation */
 uint64_t og_launch_count(const og_ctx* ctx);
+/* per-kernel timing: CUDA events around every launch while enabled; og_profile_dump synchronises and
+ * writes "kernel,launches,total_ms" lines accumulated since the previous dump */
+int32_t og_profile(og_ctx* ctx, int32_t enable);
+int32_t og_profile_dump(og_ctx* ctx, char* buf, uint64_t cap);
 /* integer-pipe micro-benchmark: achieved 32-bit multiply-add lane-ops per second */
 int32_t og_imad_peak(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s);
 

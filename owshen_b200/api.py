@@ -43,6 +43,8 @@ _SIGS = {
     "og_timer_start": (C.c_int32, [C.c_void_p]),
     "og_timer_stop": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "og_launch_count": (C.c_uint64, [C.c_void_p]),
+    "og_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "og_profile_dump": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "og_imad_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "og_field_op": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_mimc7_constants": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
@@ -150,6 +152,19 @@ class Context:
     @property
     def launch_count(self) -> int:
         return lib().og_launch_count(self._h)
+
+    def profile(self, enable: bool):
+        _check(lib().og_profile(self._h, int(enable)), self)
+
+    def profile_dump(self) -> dict:
+        """{kernel: (launches, total_ms)} since the previous dump (synchronises the stream)."""
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().og_profile_dump(self._h, buf, len(buf)), self)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.rsplit(",", 2)
+            out[name] = (int(n), float(ms))
+        return out
 
     def imad_peak(self):
         a, b = C.c_double(), C.c_double()

@@ -32,6 +32,13 @@ void* og_ctx::slot(int id, size_t bytes) {
     return slot_ptr[id];
 }
 
+cudaEvent_t og_ctx::prof_event() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
 namespace og {
 int32_t clear_flag(og_ctx* ctx) {
     OG_CUDA(ctx, cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), ctx->stream));
@@ -98,6 +105,8 @@ void og_free(og_ctx* ctx) {
     if (ctx->g2_fixed) cudaFree(ctx->g2_fixed);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -122,6 +131,37 @@ int32_t og_timer_stop(og_ctx* ctx, float* ms) {
     return OG_OK;
 }
 uint64_t og_launch_count(const og_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t og_profile(og_ctx* ctx, int32_t enable) {
+    if (!ctx) return OG_E_INVALID;
+    ctx->prof_on = enable != 0;
+    return OG_OK;
+}
+// "name,launches,total_ms\n" per kernel since the last dump; synchronises the stream
+int32_t og_profile_dump(og_ctx* ctx, char* buf, uint64_t cap) {
+    if (!ctx || !buf || cap == 0) return OG_E_INVALID;
+    OG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    struct Agg { const char* name; uint64_t n; double ms; };
+    std::vector<Agg> agg;
+    for (auto& r : ctx->prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        size_t k = 0;
+        for (; k < agg.size(); k++) if (strcmp(agg[k].name, r.name) == 0) break;
+        if (k == agg.size()) agg.push_back({r.name, 0, 0.0});
+        agg[k].n++; agg[k].ms += ms;
+        ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    uint64_t off = 0;
+    buf[0] = 0;
+    for (auto& a : agg) {
+        int w = snprintf(buf + off, cap - off, "%s,%llu,%.6f\n", a.name, (unsigned long long)a.n, a.ms);
+        if (w < 0 || (uint64_t)w >= cap - off) break;
+        off += (uint64_t)w;
+    }
+    return OG_OK;
+}
 
 // ---- field probes --------------------------------------------------------------------------------------
 }  // extern "C"

@@ -34,6 +34,13 @@ struct og_ctx {
     void* g1_fixed = nullptr;        // fixed-base tables of the generators (setup only)
     void* g2_fixed = nullptr;
 
+    // optional per-kernel timing: CUDA events around every launch of this library (og_profile)
+    bool prof_on = false;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t prof_event();
+
     void* slot(int id, size_t bytes);   // nullptr on allocation failure (err is set)
 };
 
@@ -56,12 +63,17 @@ namespace og {
     } while (0)
 
 // every kernel launch of the library goes through this so og_launch_count is exact
-#define OG_LAUNCH(ctx, kernel, grid, block, smem, ...)                                            \
+#define OG_LAUNCHN(ctx, name, kernel, grid, block, smem, ...)                                     \
     do {                                                                                          \
+        cudaEvent_t pa_ = nullptr, pb_ = nullptr;                                                 \
+        if ((ctx)->prof_on) { pa_ = (ctx)->prof_event(); pb_ = (ctx)->prof_event();               \
+                              cudaEventRecord(pa_, (ctx)->stream); }                              \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
+        if (pa_) { cudaEventRecord(pb_, (ctx)->stream); (ctx)->prof.push_back({(name), pa_, pb_}); } \
         (ctx)->launches++;                                                                        \
         OG_CUDA(ctx, cudaGetLastError());                                                         \
     } while (0)
+#define OG_LAUNCH(ctx, kernel, grid, block, smem, ...) OG_LAUNCHN(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 
 #define OG_SLOT(ctx, var, type, id, bytes)                       \
     type* var = (type*)(ctx)->slot((id), (bytes));               \

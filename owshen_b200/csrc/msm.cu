@@ -266,9 +266,9 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     OG_CUDA(ctx, cudaMemsetAsync(d_heavy, 0, sizeof(uint32_t), ctx->stream));
     // cap: a bucket that would keep one thread busy far longer than its warp-mates goes to a CTA
     uint32_t cap = 4096;
-    OG_LAUNCH(ctx, k_bucket_acc<F>, (n_keys + 127) / 128, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy);
+    OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_bucket_acc_g1" : "k_bucket_acc_g2", k_bucket_acc<F>, (n_keys + 127) / 128, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy);
     auto k_heavy = k_bucket_heavy<F, HT>;
-    OG_LAUNCH(ctx, k_heavy, ctx->sm_count, HT, HT * sizeof(XYZZ<F>), d_table, d_sorted, d_offsets, d_counts, d_buckets, d_heavy);
+    OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_bucket_heavy_g1" : "k_bucket_heavy_g2", k_heavy, ctx->sm_count, HT, HT * sizeof(XYZZ<F>), d_table, d_sorted, d_offsets, d_counts, d_buckets, d_heavy);
     // reduction levels
     size_t lvl_stride = (size_t)n_groups * ((nb + 31) / 32) + 16;
     XYZZ<F>* bufS[2] = {d_lvl, d_lvl + lvl_stride};
@@ -280,7 +280,7 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     do {
         uint32_t n_out = (n_in + 31) / 32;
         uint32_t threads = n_groups * n_out;
-        OG_LAUNCH(ctx, k_reduce_level<F>, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]);
+        OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2", k_reduce_level<F>, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]);
         S_in = bufS[pp]; U_in = bufU[pp];
         pp ^= 1;
         n_in = n_out;

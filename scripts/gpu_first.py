@@ -53,6 +53,13 @@ def _():
         assert e.code == -2
 
 
+def _root64(leaves):
+    cur = cport.unfr(leaves)
+    while len(cur) > 1:
+        cur = [mimc7.hash2(cur[2 * i], cur[2 * i + 1]) for i in range(len(cur) // 2)]
+    return bn.fr_to_bytes(cur[0])
+
+
 @stage("mimc")
 def _():
     xs = [random.randrange(R) for _ in range(64)]; ys = [random.randrange(R) for _ in range(64)]
@@ -69,13 +76,6 @@ def _():
     print(f"  merkle 4096x32: gpu first {t1*1e3:.1f} ms, second {t2*1e3:.1f} ms (host wall), cpu oracle {t3*1e3:.0f} ms ({cport.lib().oc_num_threads()} thr)")
     lv = ctx.merkle_build(leaves[:32 * 64])
     assert lv[-32:] == _root64(leaves[:32 * 64])
-
-
-def _root64(leaves):
-    cur = cport.unfr(leaves)
-    while len(cur) > 1:
-        cur = [mimc7.hash2(cur[2 * i], cur[2 * i + 1]) for i in range(len(cur) // 2)]
-    return bn.fr_to_bytes(cur[0])
 
 
 @stage("ntt")
