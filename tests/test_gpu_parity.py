@@ -1,0 +1,285 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the oracle on the same seeded
+inputs (bit-exact: this is integer / byte work), plus size-independent properties at BASELINE sizes."""
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+import owshen_b200 as ob
+from owshen_b200 import api
+from oracle import bn254 as bn
+from oracle import cport, mimc7
+from oracle import withdraw_circuit as wc
+from tests.helpers import pk_blob, rand_fr_bytes, rand_g1, rand_g2, rand_inputs, vk_blob
+
+pytestmark = pytest.mark.gpu
+R, P = bn.R, bn.P
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+
+
+def test_library_is_the_cuda_one(ctx):
+    n0 = ctx.launch_count
+    ctx.field_op("fr", "mul", bn.fr_to_bytes(3), bn.fr_to_bytes(5))
+    assert ctx.launch_count == n0 + 1
+    a, b = ctx.imad_peak()
+    assert a > 1e12 and b > 1e12
+
+
+def test_field_ops_ptx_path(ctx):
+    rng = random.Random(1)
+    for F, mod, pack in (("fq", P, cport.fqs), ("fr", R, cport.frs)):
+        xs = [rng.randrange(mod) for _ in range(20000)] + [0, 1, mod - 1, mod - 1, 2**253, mod - 2, 2**32 - 1]
+        ys = [rng.randrange(mod) for _ in range(20000)] + [mod - 1, mod - 1, mod - 1, 1, 2**253, mod - 2, 2**224]
+        assert cport.unfr(ctx.field_op(F, "mul", pack(xs), pack(ys))) == [a * b % mod for a, b in zip(xs, ys)]
+        assert cport.unfr(ctx.field_op(F, "add", pack(xs), pack(ys))) == [(a + b) % mod for a, b in zip(xs, ys)]
+        assert cport.unfr(ctx.field_op(F, "sub", pack(xs), pack(ys))) == [(a - b) % mod for a, b in zip(xs, ys)]
+    for v in GOLD["field"]:
+        pack = cport.fqs if v["field"] == "fq" else cport.frs
+        a, b = pack([int(x) for x in v["a"]]), pack([int(x) for x in v["b"]])
+        for op in ("mul", "add", "sub"):
+            assert cport.unfr(ctx.field_op(v["field"], op, a, b)) == [int(x) for x in v[op]]
+    with pytest.raises(ob.OwshenB200Error) as e:
+        ctx.field_op("fr", "mul", R.to_bytes(32, "little"), bytes(32))
+    assert e.value.code == -2
+
+
+def test_mimc7_hash_and_merkle_paths(ctx):
+    rng = random.Random(2)
+    xs = [rng.randrange(R) for _ in range(100)] + [0, 1, R - 1]
+    ys = [rng.randrange(R) for _ in range(100)] + [0, 2, R - 1]
+    assert cport.unfr(ctx.mimc7_hash2(cport.frs(xs), cport.frs(ys))) == [cport.mimc7_multi_hash([a, b]) for a, b in zip(xs, ys)]
+    assert mimc7.hash2(xs[0], ys[0]) == cport.mimc7_multi_hash([xs[0], ys[0]])
+    g = GOLD["mimc7"]
+    assert cport.unfr(ctx.mimc7_hash2(cport.frs([1]), cport.frs([2])))[0] == int(g["multi_hash_1_2"])
+    pth = g["path"]
+    got = cport.unfr(ctx.merkle_paths(cport.frs([int(pth["leaf"])]), cport.frs([int(x) for x in pth["siblings"]]), [pth["bits"]], 3))
+    assert got == [int(x) for x in pth["nodes"]]
+    for n, depth in ((1, 1), (5, 7), (300, 32)):
+        leaves, sib = rand_fr_bytes(rng, n), rand_fr_bytes(rng, n * depth)
+        bits = [rng.randrange(1 << depth) for _ in range(n)]
+        assert ctx.merkle_paths(leaves, sib, bits, depth) == cport.merkle_paths(leaves, sib, bits, depth)
+    assert ctx.merkle_paths(b"", b"", [], 5) == b""
+
+
+def test_merkle_paths_config2_full_size(ctx):
+    """BASELINE config 2: 4096 leaves x depth 32, bit-exact vs the oracle."""
+    rng = random.Random(3)
+    n, depth = 4096, 32
+    leaves, sib = rand_fr_bytes(rng, n), rand_fr_bytes(rng, n * depth)
+    bits = [rng.randrange(1 << 32) for _ in range(n)]
+    assert ctx.merkle_paths(leaves, sib, bits, depth) == cport.merkle_paths(leaves, sib, bits, depth)
+
+
+def test_merkle_tree_api(ctx):
+    rng = random.Random(4)
+    leaves = [rng.randrange(R) for _ in range(4)]
+    t = ob.MerkleTree(ctx, 2)
+    t.insert_batch(leaves)
+    ref = mimc7.MerkleTree(2)
+    for l in leaves:
+        ref.insert(l)
+    assert int.from_bytes(t.root(), "little") == ref.root()
+    gl = [int(x) for x in GOLD["mimc7"]["tree4_leaves"]]
+    tg = ob.MerkleTree(ctx, 2); tg.insert_batch(gl)
+    assert int.from_bytes(tg.root(), "little") == int(GOLD["mimc7"]["tree4_root"])
+    # deeper sparse tree: incremental inserts, paths re-derive the root on the GPU
+    t = ob.MerkleTree(ctx, 20); ref = mimc7.MerkleTree(20)
+    vals = [rng.randrange(R) for _ in range(9)]
+    t.insert_batch(vals[:5]); t.insert(vals[5]); t.insert_batch(vals[6:])
+    for v in vals:
+        ref.insert(v)
+    assert int.from_bytes(t.root(), "little") == ref.root()
+    sibs, bits = t.path(6)
+    nodes = ctx.merkle_paths(bn.fr_to_bytes(vals[6]), sibs, [bits], 20)
+    assert nodes[-32:] == t.root()
+    lv = ctx.merkle_build(cport.frs(vals[:8]))
+    r8 = mimc7.MerkleTree(3)
+    for v in vals[:8]:
+        r8.insert(v)
+    assert int.from_bytes(lv[-32:], "little") == r8.root()
+
+
+def test_ntt_matches_oracle_all_modes(ctx):
+    rng = random.Random(5)
+    for log_n in (0, 1, 2, 3, 7, 10, 11, 12, 15, 16):
+        n = 1 << log_n
+        batch = 3 if log_n <= 12 else 2
+        data = rand_fr_bytes(rng, n * batch)
+        for inv in (False, True):
+            for co in (False, True):
+                got = ctx.ntt(data, log_n, batch, inv, co)
+                exp = b"".join(cport.ntt(data[32 * n * b:32 * n * (b + 1)], inv, co) for b in range(batch))
+                assert got == exp, (log_n, inv, co)
+    for v in GOLD["ntt"]:
+        r2 = random.Random(v["seed"])
+        data = cport.frs([r2.randrange(R) for _ in range(1 << v["log_n"])])
+        got = ctx.ntt(data, v["log_n"], 1, v["inverse"], v["coset"])
+        assert hashlib.sha256(got).hexdigest() == v["sha256"]
+
+
+def test_ntt_properties_2_20(ctx):
+    """Size-independent properties at n = 2^20: round trip and linearity (oracle-free)."""
+    rng = random.Random(6)
+    log_n, n = 20, 1 << 20
+    a, b = rand_fr_bytes(rng, n), rand_fr_bytes(rng, n)
+    fa = ctx.ntt(a, log_n, 1, False, True)
+    assert ctx.ntt(fa, log_n, 1, True, True) == a
+    fb = ctx.ntt(b, log_n)
+    fa0 = ctx.ntt(a, log_n)
+    ab = ctx.field_op("fr", "add", a, b)
+    assert ctx.ntt(ab, log_n) == ctx.field_op("fr", "add", fa0, fb)
+    assert fa0 == cport.ntt(a)            # and the oracle agrees at full size
+
+
+def test_msm_edge_cases(ctx):
+    rng = random.Random(7)
+    for n in (0, 1, 2, 3, 33, 255, 1024, 5000):
+        pts = rand_g1(rng, n)
+        sc = [rng.randrange(R) for _ in range(n)]
+        if n >= 3:
+            sc[0] = 0; sc[1] = 1; sc[2] = R - 1
+        if n >= 33:
+            pts = pts[:64 * 5] + pts[64 * 4:64 * 5] + pts[64 * 6:]      # duplicate point
+            pts = pts[:64 * 7] + bytes(64) + pts[64 * 8:]                 # point at infinity
+        assert ctx.msm_g1(pts, cport.frs(sc)) == cport.g1_msm(pts, cport.frs(sc)), n
+    for n in (0, 1, 2, 77, 600):
+        pts = rand_g2(rng, n)
+        sc = cport.frs([rng.randrange(R) for _ in range(n)])
+        assert ctx.msm_g2(pts, sc) == cport.g2_msm(pts, sc), n
+    for v in GOLD["msm"]:
+        f = ctx.msm_g1 if v["curve"] == "g1" else ctx.msm_g2
+        assert f(bytes.fromhex(v["points"]), bytes.fromhex(v["scalars"])).hex() == v["out"]
+    n = 20000                                                            # all-equal points and scalars: P+P in every bucket
+    pts = rand_g1(rng, 1) * n
+    sc = cport.frs([7] * n)
+    assert ctx.msm_g1(pts, sc) == cport.g1_msm(pts, sc)
+    pts = rand_g1(rng, n)                                                # witness-like scalars: heavy buckets
+    sc = cport.frs([rng.choice([0, 1, 1, rng.randrange(1 << 64), rng.randrange(R)]) for _ in range(n)])
+    assert ctx.msm_g1(pts, sc) == cport.g1_msm(pts, sc)
+    with pytest.raises(ob.OwshenB200Error):
+        ctx.msm_g1(pts[:64], R.to_bytes(32, "little"))
+    s9 = rand_g1(rng, 9)
+    exp = bytes(64)
+    for i in range(9):
+        exp = cport.g1_add(exp, s9[64 * i:64 * i + 64])
+    assert ctx.g1_sum(s9) == exp
+    s5 = rand_g2(rng, 5)
+    exp = bytes(128)
+    for i in range(5):
+        exp = cport.g2_add(exp, s5[128 * i:128 * i + 128])
+    assert ctx.g2_sum(s5) == exp
+
+
+def test_msm_config3_2_20(ctx):
+    """BASELINE config 3: 2^20-point G1 MSM, uniform and witness-like scalars, bit-exact vs the CPU MSM;
+    plus linearity msm(P, a) + msm(P, b) == msm(P, a + b)."""
+    rng = random.Random(8)
+    n = 1 << 20
+    pts = rand_g1(rng, n)
+    a = rand_fr_bytes(rng, n)
+    ra = ctx.msm_g1(pts, a)
+    assert ra == cport.g1_msm(pts, a)
+    wl = bytearray(rand_fr_bytes(rng, n))
+    for i in range(n):                     # 60 % in {0,1}, 30 % < 2^64, 10 % uniform
+        u = rng.random()
+        if u < 0.6:
+            wl[32 * i:32 * i + 32] = (rng.randrange(2)).to_bytes(32, "little")
+        elif u < 0.9:
+            wl[32 * i + 8:32 * i + 32] = bytes(24)
+    wl = bytes(wl)
+    rb = ctx.msm_g1(pts, wl)
+    assert rb == cport.g1_msm(pts, wl)
+    ab = ctx.field_op("fr", "add", a, wl)
+    assert ctx.msm_g1(pts, ab) == cport.g1_add(ra, rb)
+
+
+def test_withdraw_witness(ctx):
+    rng = random.Random(9)
+    for depth, batch in ((1, 2), (2, 3), (32, 5)):
+        nul, sec, rec, sib, bits = rand_inputs(rng, batch, depth)
+        assert ctx.withdraw_witness(depth, nul, sec, rec, sib, bits) == cport.withdraw_witness(nul, sec, rec, sib, bits, depth)
+
+
+@pytest.fixture(scope="module")
+def keys32(ctx):
+    rng = random.Random(10)
+    tw = [rng.randrange(1, R) for _ in range(5)]
+    pk, vk = ob.setup_withdraw(ctx, 32, *tw)
+    cs = wc.build_r1cs(32)
+    pkb, vkb = cport.setup_bytes(cs, *tw)
+    return pk, vk, cs, pkb, vkb
+
+
+def test_setup_matches_oracle(ctx, keys32):
+    pk, vk, cs, pkb, vkb = keys32
+    assert vk == vk_blob(vkb)
+    assert pk == pk_blob(cs, pkb, 32)
+    rng = random.Random(11)
+    tw = [rng.randrange(1, R) for _ in range(5)]
+    pk2, vk2 = ob.setup_withdraw(ctx, 2, *tw)
+    cs2 = wc.build_r1cs(2)
+    pkb2, vkb2 = cport.setup_bytes(cs2, *tw)
+    assert pk2 == pk_blob(cs2, pkb2, 2) and vk2 == vk_blob(vkb2)
+    with pytest.raises(ob.OwshenB200Error):
+        ob.setup_withdraw(ctx, 2, 1, 2, 3, 4, 5)         # tau = 1 lies in the evaluation domain
+
+
+def test_groth16_golden_proof(ctx):
+    g = GOLD["groth16"]
+    depth = g["depth"]
+    pk, vk = ob.setup_withdraw(ctx, depth, *[int(x) for x in g["toxic"]])
+    v = g["vk"]
+    assert vk[12:].hex() == v["alpha1"] + v["beta2"] + v["gamma2"] + v["delta2"] + v["ic"]
+    PK = ob.ProvingKey(ctx, pk)
+    f = lambda k: bn.fr_to_bytes(int(g[k]))
+    proofs, pub = ob.prove(PK, f("nullifier"), f("secret"), f("recipient"), f("sibling"), [g["bits"]], f("r") + f("s"))
+    assert proofs.hex() == g["proof"]
+    assert cport.unfr(pub) == [int(x) for x in g["public"]]
+    assert ob.verify(vk, pub, proofs)
+    wit = ctx.withdraw_witness(depth, f("nullifier"), f("secret"), f("recipient"), f("sibling"), [g["bits"]])
+    assert hashlib.sha256(wit).hexdigest() == g["witness_sha256"]
+    PK.close()
+
+
+def test_groth16_prove_bit_exact_vs_oracle(ctx, keys32):
+    pk, vk, cs, pkb, vkb = keys32
+    rng = random.Random(12)
+    PK = ob.ProvingKey(ctx, pk)
+    assert (PK.n_vars, PK.n_pub, PK.log_m, PK.depth) == (cs.n_vars, 3, 15, 32)
+    batch = 70                                   # spans two chunks of the prover (default chunk 64)
+    nul, sec, rec, sib, bits = rand_inputs(rng, batch, 32)
+    rs = cport.frs([rng.randrange(R) for _ in range(2 * batch)])
+    wit = cport.withdraw_witness(nul, sec, rec, sib, bits, 32)
+    opr = cport.Prover(cs, pkb)
+    assert PK.h_evals(wit[:32 * cs.n_vars]) == opr.h_evals(wit[:32 * cs.n_vars])
+    proofs, pub = ob.prove(PK, nul, sec, rec, sib, bits, rs)
+    nck = 12
+    idx = [0, 1, 2, 3, 4, 5, 62, 63, 64, 65, 68, 69]
+    w_sel = b"".join(wit[32 * cs.n_vars * i:32 * cs.n_vars * (i + 1)] for i in idx)
+    rs_sel = b"".join(rs[64 * i:64 * i + 64] for i in idx)
+    exp = opr.prove_batch(w_sel, rs_sel)
+    for k, i in enumerate(idx):
+        assert proofs[256 * i:256 * i + 256] == exp[256 * k:256 * k + 256], i
+    for i in (0, 63, 64, 69):
+        p, x = proofs[256 * i:256 * i + 256], pub[96 * i:96 * i + 96]
+        assert x == wit[32 * cs.n_vars * i + 32:32 * cs.n_vars * i + 128]
+        assert ob.verify(vk, x, p)
+        bad = bytearray(x); bad[40] ^= 1
+        assert not ob.verify(vk, bytes(bad), p)
+    assert PK.prove_witnesses(wit[:32 * cs.n_vars * 3], rs[:192]) == proofs[:768]
+    # r = s = 0 and identical inputs in one batch
+    z = ob.prove(PK, nul[:32] * 2, sec[:32] * 2, rec[:32] * 2, sib[:32 * 32] * 2, bits[:1] * 2, bytes(128))[0]
+    assert z[:256] == z[256:] == opr.prove(wit[:32 * cs.n_vars], 0, 0)
+    with pytest.raises(ob.OwshenB200Error):
+        ob.prove(PK, R.to_bytes(32, "little"), sec[:32], rec[:32], sib[:32 * 32], bits[:1], rs[:64])
+    PK.close()
+
+
+def test_pk_blob_rejects_garbage(ctx, keys32):
+    pk = keys32[0]
+    with pytest.raises(ob.OwshenB200Error):
+        ob.ProvingKey(ctx, b"NOPE" + pk[4:])
+    with pytest.raises(ob.OwshenB200Error):
+        ob.ProvingKey(ctx, pk[:len(pk) // 2])
