@@ -101,7 +101,10 @@ OG_HD void final_sub(uint32_t* r) {
 }
 
 // One interleaved Montgomery row.  E is the array aligned at limb 0, O the one aligned at limb 1;
-// on entry (when !first) O is the previous row's E whose limb 0 is zero, i.e. O[1] sits at limb 0.
+// on entry (when !first) O is the previous row's E whose limb 0 is zero, i.e. O[1] sits at limb 0 (the
+// "orphan") and O[2..7] at limbs 1..6.  Every multiply chain starts with mad.lo.cc so that ptxas fuses
+// the (lo, hi) pairs into IMAD.WIDE.U32(.X); the orphan is folded with a plain add ripple, which runs on
+// the ALU pipe beside the multiplier pipe (checked with cuobjdump: 125 IMAD.WIDE + 15 IMAD per product).
 template <class P>
 OG_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bool first) {
     CC cc;
@@ -114,14 +117,18 @@ OG_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bo
             O[j + 1] = mul_hi(a[j + 1], bi);
         }
     } else {
-        E[0] = add_cc(E[0], O[1], cc);
+        uint32_t orphan = O[1];
+        // O' = (O >> 2 limbs) + a_odd * bi
+        O[0] = mad_lo_cc(a[1], bi, O[2], cc);
+        O[1] = madc_hi_cc(a[1], bi, O[3], cc);
 #pragma unroll
-        for (int j = 0; j < 6; j += 2) {
+        for (int j = 2; j < 6; j += 2) {
             O[j] = madc_lo_cc(a[j + 1], bi, O[j + 2], cc);
             O[j + 1] = madc_hi_cc(a[j + 1], bi, O[j + 3], cc);
         }
         O[6] = madc_lo_cc(a[7], bi, 0u, cc);
         O[7] = madc_hi(a[7], bi, 0u, cc);
+        // E += a_even * bi ; carry lands on limb 8 = O[7]
         E[0] = mad_lo_cc(a[0], bi, E[0], cc);
         E[1] = madc_hi_cc(a[0], bi, E[1], cc);
 #pragma unroll
@@ -129,6 +136,11 @@ OG_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bo
             E[j] = madc_lo_cc(a[j], bi, E[j], cc);
             E[j + 1] = madc_hi_cc(a[j], bi, E[j + 1], cc);
         }
+        O[7] = addc(O[7], 0u, cc);
+        // E += orphan (limb 0), rippled
+        E[0] = add_cc(E[0], orphan, cc);
+#pragma unroll
+        for (int j = 1; j < 8; j++) E[j] = addc_cc(E[j], 0u, cc);
         O[7] = addc(O[7], 0u, cc);
     }
     uint32_t q = mul_lo(E[0], P::INV);

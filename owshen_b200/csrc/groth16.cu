@@ -322,15 +322,17 @@ struct ChunkBufs {
     uint32_t w_stride, bsc_stride, csc_stride;
 };
 
-static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t B, ChunkBufs& b) {
+// W, rs_m and the per-proof totals cover the whole batch (the sequential witness chain and the final
+// s*A are latency-bound per thread, so they run once per batch); everything else is per chunk of B proofs.
+static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_t B, ChunkBufs& b) {
     const uint32_t m = 1u << pk->log_m;
     b.w_stride = pk->n_vars + 2;
     b.bsc_stride = pk->nB;
     b.csc_stride = pk->nC;
     size_t max_pts = pk->nC > pk->nA ? pk->nC : pk->nA;
     size_t n_keys = (size_t)B * pk->nb;
-    b.W = (Fr*)ctx->slot(S_PR_WIT, sizeof(Fr) * (size_t)B * b.w_stride);
-    b.rs_m = (Fr*)ctx->slot(S_PR_MISC, sizeof(Fr) * 2 * (size_t)B);
+    b.W = (Fr*)ctx->slot(S_PR_WIT, sizeof(Fr) * (size_t)batch * b.w_stride);
+    b.rs_m = (Fr*)ctx->slot(S_PR_MISC, sizeof(Fr) * 2 * (size_t)batch);
     b.abc = (Fr*)ctx->slot(S_PR_ABC, sizeof(Fr) * (size_t)B * 3 * m * 2);
     b.bsc = (Fr*)ctx->slot(S_PR_SCALARS, sizeof(Fr) * (size_t)B * (b.bsc_stride + b.csc_stride));
     b.sorted = (uint32_t*)ctx->slot(S_PR_SORTED, 4 * (size_t)B * max_pts * pk->n_windows);
@@ -340,15 +342,15 @@ static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t B, ChunkBufs& 
     b.heavy = (uint32_t*)ctx->slot(S_PR_HEAVY, 4 * (n_keys + 1));
     b.bk2 = (G2XYZZ*)ctx->slot(S_PR_BUCKETS, sizeof(G2XYZZ) * n_keys);
     b.lvl2 = (G2XYZZ*)ctx->slot(S_PR_SEG, sizeof(G2XYZZ) * msm_lvl_elems(B, pk->nb));
-    b.totA = (G1XYZZ*)ctx->slot(S_PR_SUMS, (sizeof(G1XYZZ) * 2 + sizeof(G2XYZZ)) * (size_t)B);
+    b.totA = (G1XYZZ*)ctx->slot(S_PR_SUMS, (sizeof(G1XYZZ) * 2 + sizeof(G2XYZZ)) * (size_t)batch);
     if (!b.W || !b.rs_m || !b.abc || !b.bsc || !b.sorted || !b.counts || !b.offsets || !b.cursor || !b.heavy || !b.bk2 || !b.lvl2 || !b.totA)
         return OG_E_NOMEM;
     b.ntt_tmp = b.abc + (size_t)B * 3 * m;
     b.csc = b.bsc + (size_t)B * b.bsc_stride;
     b.bk1 = reinterpret_cast<G1XYZZ*>(b.bk2);       // the G1 and G2 MSMs of a chunk run one after another
     b.lvl1 = reinterpret_cast<G1XYZZ*>(b.lvl2);
-    b.totC = b.totA + B;
-    b.totB = reinterpret_cast<G2XYZZ*>(b.totC + B);
+    b.totC = b.totA + batch;
+    b.totB = reinterpret_cast<G2XYZZ*>(b.totC + batch);
     return OG_OK;
 }
 
@@ -377,28 +379,39 @@ static int32_t run_msm_g2(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t B
     return msm_buckets_g2(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb, b.bk2, b.lvl2, b.heavy, totals);
 }
 
-// everything after the witness rows W[B][n_vars] are in place
-static int32_t prove_chunk(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t B, const uint8_t* d_rs, uint8_t* d_proofs) {
+// proofs [off, off+B): everything between the witness rows (already in b.W) and the per-proof MSM totals
+static int32_t prove_chunk(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t off, uint32_t B) {
     const uint32_t m = 1u << pk->log_m, n_priv = pk->n_vars - pk->n_pub - 1;
-    OG_LAUNCH(ctx, k_extras, (B + 127) / 128, 128, 0, d_rs, B, pk->n_vars, b.w_stride, b.W, b.rs_m, ctx->d_flag);
+    const Fr* W = b.W + (size_t)off * b.w_stride;
+    const Fr* rs_m = b.rs_m + 2 * (size_t)off;
     CsrDev A{pk->a_ptr, pk->a_col, pk->a_val}, Bm{pk->b_ptr, pk->b_col, pk->b_val};
-    OG_LAUNCH(ctx, k_abc, dim3((m + 127) / 128, B), 128, 0, A, Bm, pk->n_constraints, pk->n_pub, pk->log_m, b.W, b.w_stride, B, b.abc);
+    OG_LAUNCH(ctx, k_abc, dim3((m + 127) / 128, B), 128, 0, A, Bm, pk->n_constraints, pk->n_pub, pk->log_m, W, b.w_stride, B, b.abc);
     OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3 * B, 1, 0));
     OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3 * B, 0, 1));
     uint32_t mx = n_priv > pk->n_supp ? n_priv : pk->n_supp;
-    OG_LAUNCH(ctx, k_compose, dim3((mx + 127) / 128, B), 128, 0, b.W, b.w_stride, b.rs_m, pk->supp, pk->n_supp, pk->n_vars, pk->n_pub, m,
+    OG_LAUNCH(ctx, k_compose, dim3((mx + 127) / 128, B), 128, 0, W, b.w_stride, rs_m, pk->supp, pk->n_supp, pk->n_vars, pk->n_pub, m,
               b.bsc, b.bsc_stride, b.csc, b.csc_stride);
     OG_LAUNCH(ctx, k_pointwise, dim3((m + 127) / 128, B), 128, 0, b.abc, pk->log_m, B, b.csc, b.csc_stride, n_priv + pk->n_supp);
-    OG_TRY(run_msm_g1(ctx, pk, b, B, pk->tabA, pk->nA, b.W, b.w_stride, b.totA));
-    OG_TRY(run_msm_g1(ctx, pk, b, B, pk->tabC, pk->nC, b.csc, b.csc_stride, b.totC));
-    OG_TRY(run_msm_g2(ctx, pk, b, B, pk->tabB, pk->nB, b.bsc, b.bsc_stride, b.totB));
-    OG_LAUNCH(ctx, k_assemble_g1, (B + 31) / 32, 32, 0, b.totA, b.totC, b.rs_m, B, d_proofs);
-    OG_LAUNCH(ctx, k_assemble_g2, (B + 31) / 32, 32, 0, b.totB, B, d_proofs);
+    OG_TRY(run_msm_g1(ctx, pk, b, B, pk->tabA, pk->nA, W, b.w_stride, b.totA + off));
+    OG_TRY(run_msm_g1(ctx, pk, b, B, pk->tabC, pk->nC, b.csc, b.csc_stride, b.totC + off));
+    OG_TRY(run_msm_g2(ctx, pk, b, B, pk->tabB, pk->nB, b.bsc, b.bsc_stride, b.totB + off));
+    return OG_OK;
+}
+
+// whole batch: extras before the chunks, assembly after them
+static int32_t prove_batch(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t batch, uint32_t CB, const uint8_t* d_rs, uint8_t* d_proofs) {
+    OG_LAUNCH(ctx, k_extras, (batch + 127) / 128, 128, 0, d_rs, batch, pk->n_vars, b.w_stride, b.W, b.rs_m, ctx->d_flag);
+    for (uint32_t off = 0; off < batch; off += CB) {
+        uint32_t B = batch - off < CB ? batch - off : CB;
+        OG_TRY(prove_chunk(ctx, pk, b, off, B));
+    }
+    OG_LAUNCH(ctx, k_assemble_g1, (batch + 31) / 32, 32, 0, b.totA, b.totC, b.rs_m, batch, d_proofs);
+    OG_LAUNCH(ctx, k_assemble_g2, (batch + 31) / 32, 32, 0, b.totB, batch, d_proofs);
     return OG_OK;
 }
 
 static uint32_t chunk_size(uint32_t batch) {
-    uint32_t c = env_u32("OG_CHUNK", 64);
+    uint32_t c = env_u32("OG_CHUNK", 256);
     return c < batch ? c : batch;
 }
 
@@ -411,37 +424,26 @@ int32_t prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_null, 
     if (L.n_vars != pk->n_vars) return OG_E_INVALID;
     uint32_t CB = chunk_size(batch);
     ChunkBufs b;
-    OG_TRY(alloc_chunk(ctx, pk, CB, b));
-    for (uint32_t off = 0; off < batch; off += CB) {
-        uint32_t B = batch - off < CB ? batch - off : CB;
-        // witness rows are written with stride n_vars+2: build them through a strided layout
-        WithdrawLayout Ls = L;
-        OG_TRY(withdraw_witness_strided_dev(ctx, Ls, b.w_stride, d_null + 32ull * off, d_sec + 32ull * off, d_rec + 32ull * off,
-                                            d_sib + 32ull * off * pk->depth, d_bits + off, B, b.W));
-        if (d_public) OG_LAUNCH(ctx, k_public_out, (B * pk->n_pub + 127) / 128, 128, 0, b.W, b.w_stride, B, pk->n_pub, d_public + 32ull * off * pk->n_pub);
-        OG_TRY(prove_chunk(ctx, pk, b, B, d_rs + 64ull * off, d_proofs + 256ull * off));
-    }
-    return OG_OK;
+    OG_TRY(alloc_chunk(ctx, pk, batch, CB, b));
+    OG_TRY(withdraw_witness_strided_dev(ctx, L, b.w_stride, d_null, d_sec, d_rec, d_sib, d_bits, batch, b.W));
+    if (d_public) OG_LAUNCH(ctx, k_public_out, (batch * pk->n_pub + 127) / 128, 128, 0, b.W, b.w_stride, batch, pk->n_pub, d_public);
+    return prove_batch(ctx, pk, b, batch, CB, d_rs, d_proofs);
 }
 
 int32_t prove_witness_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_wit, uint32_t batch, const uint8_t* d_rs, uint8_t* d_proofs) {
     if (batch == 0) return OG_OK;
     uint32_t CB = chunk_size(batch);
     ChunkBufs b;
-    OG_TRY(alloc_chunk(ctx, pk, CB, b));
-    for (uint32_t off = 0; off < batch; off += CB) {
-        uint32_t B = batch - off < CB ? batch - off : CB;
-        uint64_t tot = (uint64_t)B * pk->n_vars;
-        OG_LAUNCH(ctx, k_witness_in, (unsigned)((tot + 127) / 128), 128, 0, d_wit + 32ull * off * pk->n_vars, B, pk->n_vars, b.w_stride, b.W, ctx->d_flag);
-        OG_TRY(prove_chunk(ctx, pk, b, B, d_rs + 64ull * off, d_proofs + 256ull * off));
-    }
-    return OG_OK;
+    OG_TRY(alloc_chunk(ctx, pk, batch, CB, b));
+    uint64_t tot = (uint64_t)batch * pk->n_vars;
+    OG_LAUNCH(ctx, k_witness_in, (unsigned)((tot + 127) / 128), 128, 0, d_wit, batch, pk->n_vars, b.w_stride, b.W, ctx->d_flag);
+    return prove_batch(ctx, pk, b, batch, CB, d_rs, d_proofs);
 }
 
 // debug / parity probe: d_j for one witness (canonical bytes on device in and out)
 int32_t h_evals_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_wit, uint8_t* d_out) {
     ChunkBufs b;
-    OG_TRY(alloc_chunk(ctx, pk, 1, b));
+    OG_TRY(alloc_chunk(ctx, pk, 1, 1, b));
     const uint32_t m = 1u << pk->log_m, n_priv = pk->n_vars - pk->n_pub - 1;
     OG_LAUNCH(ctx, k_witness_in, (pk->n_vars + 127) / 128, 128, 0, d_wit, 1, pk->n_vars, b.w_stride, b.W, ctx->d_flag);
     CsrDev A{pk->a_ptr, pk->a_col, pk->a_val}, Bm{pk->b_ptr, pk->b_col, pk->b_val};
