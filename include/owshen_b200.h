@@ -65,6 +65,9 @@ int32_t og_profile(og_ctx* ctx, int32_t enable);
 int32_t og_profile_dump(og_ctx* ctx, char* buf, uint64_t cap);
 /* integer-pipe micro-benchmark: achieved 32-bit multiply-add lane-ops per second */
 int32_t og_imad_peak(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s);
+/* same plus the rate of 32x32->64 multiply-adds issued as mad.lo.cc/madc.hi.cc carry chains (the shape of
+ * a Montgomery row, IMAD.WIDE.U32.X): the honest roofline denominator of the field multiplier */
+int32_t og_int_pipe_peaks(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s, double* carry_chain_wide_per_s);
 
 /* ---- element-wise field ops (parity probes for the limb arithmetic) ------------------------- */
 /* field: 0 = Fq, 1 = Fr; op: 0 = mul, 1 = add, 2 = sub */
@@ -93,6 +96,9 @@ int32_t og_msm_g1(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, ui
 int32_t og_msm_g2(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out128);
 int32_t og_msm_g1_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out64);
 int32_t og_msm_g2_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out128);
+/* out_points[i] = scalars[i] * G for the standard generators (fixed-base windows on the GPU) */
+int32_t og_g1_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uint8_t* out_points64);
+int32_t og_g2_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uint8_t* out_points128);
 /* plain sums of affine points: the local step after the multi-GPU all-gather of partial MSMs */
 int32_t og_g1_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out64);
 int32_t og_g2_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out128);

@@ -46,6 +46,7 @@ _SIGS = {
     "og_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
     "og_profile_dump": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "og_imad_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "og_int_pipe_peaks": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "og_field_op": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_mimc7_constants": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "og_mimc7_hash2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
@@ -56,6 +57,8 @@ _SIGS = {
     "og_msm_g2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_msm_g1_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_msm_g2_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_g1_generator_mul": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_g2_generator_mul": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_g1_sum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_g2_sum": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_ntt": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32]),
@@ -171,6 +174,11 @@ class Context:
         _check(lib().og_imad_peak(self._h, C.byref(a), C.byref(b)), self)
         return a.value, b.value
 
+    def int_pipe_peaks(self) -> dict:
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(lib().og_int_pipe_peaks(self._h, C.byref(a), C.byref(b), C.byref(c)), self)
+        return {"imad_per_s": a.value, "imad_wide_per_s": b.value, "imad_wide_carry_chain_per_s": c.value}
+
     # ---- probes / kernels on host buffers -------------------------------------------------------
     def field_op(self, field: str, op: str, a: bytes, b: bytes) -> bytes:
         n = len(a) // 32
@@ -209,6 +217,18 @@ class Context:
         assert len(points) == 128 * n
         out = C.create_string_buffer(128)
         _check(lib().og_msm_g2(self._h, points, scalars, n, out), self)
+        return out.raw
+
+    def g1_generator_mul(self, scalars: bytes) -> bytes:
+        n = len(scalars) // 32
+        out = C.create_string_buffer(64 * n)
+        _check(lib().og_g1_generator_mul(self._h, scalars, n, out), self)
+        return out.raw
+
+    def g2_generator_mul(self, scalars: bytes) -> bytes:
+        n = len(scalars) // 32
+        out = C.create_string_buffer(128 * n)
+        _check(lib().og_g2_generator_mul(self._h, scalars, n, out), self)
         return out.raw
 
     def g1_sum(self, points: bytes) -> bytes:

@@ -177,44 +177,67 @@ __global__ void __launch_bounds__(128) k_field_op(int op, const uint8_t* __restr
     store_canonical(out + 32 * i, r);
 }
 
-// integer-pipe micro-benchmark: long dependent-free chains of 32-bit multiply-adds
-template <int WIDE>
+// integer-pipe micro-benchmark.  Every multiply-add takes its own accumulator as a multiplicand, so ptxas
+// cannot hoist the product out of the loop (an earlier version with loop-invariant multiplicands was
+// strength-reduced to additions and measured the ALU pipe instead).  MODE 0: mad.lo.u32 (IMAD),
+// MODE 1: mad.wide.u32 (IMAD.WIDE), MODE 2: mad.lo.cc/madc.hi.cc pairs in 4-pair carry chains, the
+// shape of one Montgomery row (IMAD.WIDE.U32.X); a pair counts as ONE 32x32->64 multiply-add.
+template <int MODE>
 __global__ void __launch_bounds__(256) k_imad(uint32_t* out, uint32_t iters, uint32_t seed) {
-    uint32_t a0 = threadIdx.x + seed, a1 = a0 * 3 + 1, a2 = a0 * 5 + 2, a3 = a0 * 7 + 3;
-    uint32_t x = blockIdx.x * 2654435761u + 12345u, y = x ^ 0x9e3779b9u;
-    if (WIDE) {
-        unsigned long long w0 = a0, w1 = a1, w2 = a2, w3 = a3, w4 = a0 ^ y, w5 = a1 ^ y, w6 = a2 ^ y, w7 = a3 ^ y;
+    uint32_t x = blockIdx.x * 2654435761u + 12345u + seed, y = x ^ 0x9e3779b9u;
+    if (MODE == 0) {
+        uint32_t w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = threadIdx.x * (2 * k + 3) + seed;
         for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w0) : "r"(x), "r"(y));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w1) : "r"(x), "r"(y));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w2) : "r"(x), "r"(y));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w3) : "r"(x), "r"(y));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w4) : "r"(x), "r"(y));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w5) : "r"(x), "r"(y));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w6) : "r"(x), "r"(y));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w7) : "r"(x), "r"(y));
-            }
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(w[k]) : "r"(x), "r"(y));
         }
-        unsigned long long s = w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s ^= w[k];
+        if (s == 0x1234567u) out[0] = s;
+    } else if (MODE == 1) {
+        unsigned long long w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) w[k] = threadIdx.x * (2 * k + 3) + seed;
+        for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    uint32_t lo = (uint32_t)w[k];
+                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[k]) : "r"(lo), "r"(x));
+                }
+        }
+        unsigned long long s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s ^= w[k];
         if (s == 0x1234567ull) out[0] = (uint32_t)s;
     } else {
-        uint32_t w0 = a0, w1 = a1, w2 = a2, w3 = a3, w4 = a0 ^ y, w5 = a1 ^ y, w6 = a2 ^ y, w7 = a3 ^ y;
+        uint32_t e[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { e[k] = threadIdx.x * (2 * k + 3) + seed; o[k] = e[k] ^ y; }
+        CC cc;
         for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w0) : "r"(x), "r"(y));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w1) : "r"(x), "r"(y));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w2) : "r"(x), "r"(y));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w3) : "r"(x), "r"(y));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w4) : "r"(x), "r"(y));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w5) : "r"(x), "r"(y));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w6) : "r"(x), "r"(y));
-                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(w7) : "r"(x), "r"(y));
+            for (int r = 0; r < 4; r++) {
+                uint32_t m0 = e[7] | 1u, m1 = o[7] | 1u;      // multiplicand depends on the previous chain
+                e[0] = mad_lo_cc(m0, x, e[0], cc); e[1] = madc_hi_cc(m0, x, e[1], cc);
+                e[2] = madc_lo_cc(m0, y, e[2], cc); e[3] = madc_hi_cc(m0, y, e[3], cc);
+                e[4] = madc_lo_cc(m0, x, e[4], cc); e[5] = madc_hi_cc(m0, x, e[5], cc);
+                e[6] = madc_lo_cc(m0, y, e[6], cc); e[7] = madc_hi(m0, y, e[7], cc);
+                o[0] = mad_lo_cc(m1, x, o[0], cc); o[1] = madc_hi_cc(m1, x, o[1], cc);
+                o[2] = madc_lo_cc(m1, y, o[2], cc); o[3] = madc_hi_cc(m1, y, o[3], cc);
+                o[4] = madc_lo_cc(m1, x, o[4], cc); o[5] = madc_hi_cc(m1, x, o[5], cc);
+                o[6] = madc_lo_cc(m1, y, o[6], cc); o[7] = madc_hi(m1, y, o[7], cc);
             }
         }
-        uint32_t s = w0 ^ w1 ^ w2 ^ w3 ^ w4 ^ w5 ^ w6 ^ w7;
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s ^= e[k] ^ o[k];
         if (s == 0x1234567u) out[0] = s;
     }
 }
@@ -224,23 +247,31 @@ extern "C" {
 
 int32_t og_imad_peak(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s) {
     if (!ctx || !mad_per_s || !wide_mad_per_s) return OG_E_INVALID;
+    double chain = 0;
+    return og_int_pipe_peaks(ctx, mad_per_s, wide_mad_per_s, &chain);
+}
+
+int32_t og_int_pipe_peaks(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s, double* carry_chain_wide_per_s) {
+    if (!ctx || !mad_per_s || !wide_mad_per_s || !carry_chain_wide_per_s) return OG_E_INVALID;
     OG_SLOT(ctx, d_out, uint32_t, S_IO_A, 64);
-    const uint32_t iters = 4096, ctas = ctx->sm_count * 8, threads = 256;
-    const double ops = (double)ctas * threads * iters * 64.0;
+    const uint32_t iters = 2048, ctas = ctx->sm_count * 8, threads = 256;
     float ms = 0;
-    for (int wide = 0; wide < 2; wide++) {
+    double* outs[3] = {mad_per_s, wide_mad_per_s, carry_chain_wide_per_s};
+    const double per_iter[3] = {64.0, 64.0, 32.0};
+    for (int mode = 0; mode < 3; mode++) {
         double best = 0;
         for (int rep = 0; rep < 4; rep++) {
             OG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-            if (wide) OG_LAUNCH(ctx, k_imad<1>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
-            else OG_LAUNCH(ctx, k_imad<0>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
+            if (mode == 0) OG_LAUNCH(ctx, k_imad<0>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
+            else if (mode == 1) OG_LAUNCH(ctx, k_imad<1>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
+            else OG_LAUNCH(ctx, k_imad<2>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
             OG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
             OG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
             OG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-            double rate = ops / (ms * 1e-3);
+            double rate = (double)ctas * threads * iters * per_iter[mode] / (ms * 1e-3);
             if (rep > 0 && rate > best) best = rate;
         }
-        if (wide) *wide_mad_per_s = best; else *mad_per_s = best;
+        *outs[mode] = best;
     }
     return OG_OK;
 }
@@ -371,6 +402,34 @@ int32_t og_g2_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out12
     if (n) H2D(ctx, dp, points, 128 * n);
     OG_TRY(sum_g2_dev(ctx, dp, n, dout));
     D2H(ctx, out128, dout, 128);
+    return check_flag(ctx);
+}
+
+// out[i] = scalars[i] * G (fixed-base, generator of G1 / G2): used by the setup and to synthesise MSM inputs
+int32_t og_g1_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uint8_t* out_points) {
+    if (!ctx || (n && (!scalars || !out_points))) return OG_E_INVALID;
+    if (n == 0) return OG_OK;
+    OG_SLOT(ctx, ds, uint8_t, S_IO_A, 32 * n);
+    OG_SLOT(ctx, dp, G1Affine, S_IO_B, sizeof(G1Affine) * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 64 * n);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, ds, scalars, 32 * n);
+    OG_TRY(fixed_base_mul_g1(ctx, ds, n, dp));
+    OG_TRY(g1_mont_to_bytes(ctx, dp, n, dout));
+    D2H(ctx, out_points, dout, 64 * n);
+    return check_flag(ctx);
+}
+int32_t og_g2_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uint8_t* out_points) {
+    if (!ctx || (n && (!scalars || !out_points))) return OG_E_INVALID;
+    if (n == 0) return OG_OK;
+    OG_SLOT(ctx, ds, uint8_t, S_IO_A, 32 * n);
+    OG_SLOT(ctx, dp, G2Affine, S_IO_B, sizeof(G2Affine) * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 128 * n);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, ds, scalars, 32 * n);
+    OG_TRY(fixed_base_mul_g2(ctx, ds, n, dp));
+    OG_TRY(g2_mont_to_bytes(ctx, dp, n, dout));
+    D2H(ctx, out_points, dout, 128 * n);
     return check_flag(ctx);
 }
 

@@ -101,13 +101,18 @@ OG_HD void final_sub(uint32_t* r) {
 }
 
 // One interleaved Montgomery row.  E is the array aligned at limb 0, O the one aligned at limb 1;
-// on entry (when !first) O is the previous row's E whose limb 0 is zero, i.e. O[1] sits at limb 0 (the
-// "orphan") and O[2..7] at limbs 1..6.  Every multiply chain starts with mad.lo.cc so that ptxas fuses
-// the (lo, hi) pairs into IMAD.WIDE.U32(.X); the orphan is folded with a plain add ripple, which runs on
-// the ALU pipe beside the multiplier pipe (checked with cuobjdump: 125 IMAD.WIDE + 15 IMAD per product).
+// on entry (when !first) O is the previous row's E: its limb 0 is dead (zero by construction), O[1] sits
+// at limb 0 (the "orphan") and O[2..7] at limbs 1..6.
+//  * every a*b chain starts with mad.lo.cc so that ptxas fuses the (lo, hi) pairs into IMAD.WIDE.U32(.X);
+//  * the orphan is folded while forming s = E[0] + orphan: its carry enters the q*p chain on O (limb 1),
+//    and because s + lo(q*p0) == 0 (mod 2^32) the low product is never computed: its carry is (s != 0),
+//    injected with add.cc(s, 0xffffffff) into the q*p chain on E, which starts at limb 1.
+// No limb ripples through a whole array, so successive rows overlap and the dependency chain per product
+// is short (this kernel family is latency-bound at 4 warps/scheduler; see profiles/).
 template <class P>
 OG_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bool first) {
     CC cc;
+    uint32_t orphan = 0;
     if (first) {
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
@@ -117,7 +122,7 @@ OG_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bo
             O[j + 1] = mul_hi(a[j + 1], bi);
         }
     } else {
-        uint32_t orphan = O[1];
+        orphan = O[1];
         // O' = (O >> 2 limbs) + a_odd * bi
         O[0] = mad_lo_cc(a[1], bi, O[2], cc);
         O[1] = madc_hi_cc(a[1], bi, O[3], cc);
@@ -137,21 +142,19 @@ OG_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bo
             E[j + 1] = madc_hi_cc(a[j], bi, E[j + 1], cc);
         }
         O[7] = addc(O[7], 0u, cc);
-        // E += orphan (limb 0), rippled
-        E[0] = add_cc(E[0], orphan, cc);
-#pragma unroll
-        for (int j = 1; j < 8; j++) E[j] = addc_cc(E[j], 0u, cc);
-        O[7] = addc(O[7], 0u, cc);
     }
-    uint32_t q = mul_lo(E[0], P::INV);
-    O[0] = mad_lo_cc(P::mod(1), q, O[0], cc);
+    uint32_t s = add_cc(E[0], orphan, cc);            // carry -> limb 1
+    uint32_t q = mul_lo(s, P::INV);
+    O[0] = madc_lo_cc(P::mod(1), q, O[0], cc);
     O[1] = madc_hi_cc(P::mod(1), q, O[1], cc);
 #pragma unroll
-    for (int j = 2; j < 8; j += 2) {
+    for (int j = 2; j < 6; j += 2) {
         O[j] = madc_lo_cc(P::mod(j + 1), q, O[j], cc);
         O[j + 1] = madc_hi_cc(P::mod(j + 1), q, O[j + 1], cc);
     }
-    E[0] = mad_lo_cc(P::mod(0), q, E[0], cc);
+    O[6] = madc_lo_cc(P::mod(7), q, O[6], cc);
+    O[7] = madc_hi(P::mod(7), q, O[7], cc);           // T < 2^288: no carry out of limb 8
+    (void)add_cc(s, 0xffffffffu, cc);                 // carry = (s != 0) = carry of s + lo(q*p0)
     E[1] = madc_hi_cc(P::mod(0), q, E[1], cc);
 #pragma unroll
     for (int j = 2; j < 8; j += 2) {
@@ -159,6 +162,7 @@ OG_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bo
         E[j + 1] = madc_hi_cc(P::mod(j), q, E[j + 1], cc);
     }
     O[7] = addc(O[7], 0u, cc);
+    E[0] = 0;                                         // dead from here on
 }
 
 // r = a * b * 2^-256 mod p   (a, b < p; r may alias a or b)
@@ -290,8 +294,6 @@ struct Fq2 {
         Fq m = a.c0 * a.c1;
         return Fq2{(a.c0 + a.c1) * (a.c0 - a.c1), m + m};
     }
-    // On the device Fq2 products are real calls: a G2 group operation inlines to >10k instructions
-    // otherwise and ptxas needs tens of minutes per kernel (measured); the call costs a few percent.
     OG_HD friend Fq2 operator*(const Fq2& a, const Fq2& b);
     OG_HD Fq2 sqr() const;
     OG_HD Fq2 neg() const { return Fq2{c0.neg(), c1.neg()}; }
@@ -304,14 +306,10 @@ struct Fq2 {
     OG_HD Fq2 mul_fq(const Fq& s) const { return Fq2{c0 * s, c1 * s}; }
 };
 
-#if defined(__CUDA_ARCH__)
-static __device__ __noinline__ void fq2_mul_ni(Fq2* r, const Fq2* a, const Fq2* b) { *r = Fq2::mul_inl(*a, *b); }
-static __device__ __noinline__ void fq2_sqr_ni(Fq2* r, const Fq2* a) { *r = Fq2::sqr_inl(*a); }
-OG_HD Fq2 operator*(const Fq2& a, const Fq2& b) { Fq2 r; fq2_mul_ni(&r, &a, &b); return r; }
-OG_HD Fq2 Fq2::sqr() const { Fq2 r; fq2_sqr_ni(&r, this); return r; }
-#else
+// Fq2 products are inlined.  Kernels keep ptxas time sane by calling the out-of-line group operations of
+// ec.cuh (xyzz_*_ni) everywhere except in the bucket-accumulation inner loop (a G2 group operation is
+// ~10k instructions; inlining several of them into one kernel once cost 30 minutes of ptxas).
 OG_HD Fq2 operator*(const Fq2& a, const Fq2& b) { return Fq2::mul_inl(a, b); }
 OG_HD Fq2 Fq2::sqr() const { return Fq2::sqr_inl(*this); }
-#endif
 
 }  // namespace og

@@ -12,6 +12,7 @@
 // All arithmetic is 8x32-bit Montgomery limbs in registers (fp.cuh); the kernels are bound by the
 // integer multiply-add pipe, not HBM: a G1 mixed add moves 64 B + 4 B and costs ~3.5k instructions.
 #include "msm.cuh"
+#include <stdlib.h>
 // Compiled twice: -DOG_MSM_G1 (G1 instantiations + the curve-independent sort) and -DOG_MSM_G2.
 #if !defined(OG_MSM_G1) && !defined(OG_MSM_G2)
 #error "compile msm.cu with -DOG_MSM_G1 or -DOG_MSM_G2"
@@ -123,25 +124,62 @@ __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restric
     }
 }
 
-// ---- 2: exclusive scan (one CTA; n <= a few million keys) ------------------------------------------------
-__global__ void __launch_bounds__(1024) k_scan(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ offsets) {
-    __shared__ uint32_t part[1024];
-    uint32_t t = threadIdx.x;
-    uint32_t chunk = (n + 1023) / 1024;
-    uint32_t lo = min(n, t * chunk), hi = min(n, lo + chunk);
-    uint32_t s = 0;
-    for (uint32_t i = lo; i < hi; i++) s += counts[i];
-    part[t] = s;
+// ---- 2: exclusive scan: tile sums -> scan of the tile sums (one CTA) -> tile rescan with offsets ----------
+constexpr uint32_t SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {   // 256 threads
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    __shared__ uint32_t block_total;
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) inc += t; }
+    if (lane == 31) warp_sums[wid] = inc;
     __syncthreads();
-    for (uint32_t d = 1; d < 1024; d <<= 1) {          // Hillis-Steele inclusive scan
-        uint32_t v = t >= d ? part[t - d] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0, winc = w;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, d); if (lane >= (uint32_t)d) winc += t; }
+        if (lane < SCAN_THREADS / 32) warp_sums[lane] = winc - w;
+        if (lane == SCAN_THREADS / 32 - 1) block_total = winc;
     }
-    uint32_t run = t ? part[t - 1] : 0;
-    for (uint32_t i = lo; i < hi; i++) { offsets[i] = run; run += counts[i]; }
-    if (t == 1023) offsets[n] = part[1023];
+    __syncthreads();
+    uint32_t r = inc - v + warp_sums[wid];
+    *total = block_total;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ tile_sums) {
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD, s = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) if (base + k < n) s += counts[base + k];
+    uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// in-place exclusive scan of up to SCAN_TILE * 64 tile sums by one CTA
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(uint32_t* __restrict__ tile_sums, uint32_t n_tiles, uint32_t* __restrict__ grand_total) {
+    uint32_t run = 0;
+    for (uint32_t base = 0; base < n_tiles; base += SCAN_THREADS) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n_tiles ? tile_sums[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < n_tiles) tile_sums[i] = run + ex;
+        run += total;
+    }
+    if (threadIdx.x == 0) *grand_total = run;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ counts, uint32_t n, const uint32_t* __restrict__ tile_sums,
+                                                            uint32_t* __restrict__ offsets) {
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t c[SCAN_PER_THREAD], s = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) { c[k] = base + k < n ? counts[base + k] : 0; s += c[k]; }
+    uint32_t total;
+    uint32_t run = tile_sums[blockIdx.x] + block_exclusive_scan(s, &total);
+#pragma unroll
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) { if (base + k < n) offsets[base + k] = run; run += c[k]; }
 }
 
 int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uint32_t* d_counts, uint32_t* d_offsets,
@@ -154,7 +192,13 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
     }
     dim3 grid((unsigned)((plan.n + 255) / 256), plan.n_problems);
     OG_LAUNCH(ctx, k_digits<false>, grid, 256, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
-    OG_LAUNCH(ctx, k_scan, 1, 1024, 0, d_counts, n_keys, d_offsets);
+    {   // offsets[n_keys] receives the grand total; the tile sums live in the cursor array (zeroed again below)
+        uint32_t n_tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
+        OG_SLOT(ctx, tile_sums, uint32_t, S_MSM_MISC, 4 * (size_t)n_tiles);
+        OG_LAUNCH(ctx, k_scan_tiles, n_tiles, SCAN_THREADS, 0, d_counts, n_keys, tile_sums);
+        OG_LAUNCH(ctx, k_scan_tile_sums, 1, SCAN_THREADS, 0, tile_sums, n_tiles, d_offsets + n_keys);
+        OG_LAUNCH(ctx, k_scan_apply, n_tiles, SCAN_THREADS, 0, d_counts, n_keys, tile_sums, d_offsets);
+    }
     OG_LAUNCH(ctx, k_digits<true>, grid, 256, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
     return OG_OK;
 }
@@ -169,8 +213,10 @@ __device__ __forceinline__ Affine<F> fetch_point(const Affine<F>* __restrict__ t
     return p;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_bucket_acc(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
+// MINB = minimum resident CTAs per SM requested from ptxas: trades registers (spills) for warps in flight;
+// the kernel is latency-bound on carry chains, so the best point is measured, not guessed (OG_ACC_OCC).
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_bucket_acc(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
                                                     const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                     uint32_t n_keys, uint32_t cap, XYZZ<F>* __restrict__ buckets,
                                                     uint32_t* __restrict__ heavy) {
@@ -266,7 +312,19 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     OG_CUDA(ctx, cudaMemsetAsync(d_heavy, 0, sizeof(uint32_t), ctx->stream));
     // cap: a bucket that would keep one thread busy far longer than its warp-mates goes to a CTA
     uint32_t cap = 4096;
-    OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_bucket_acc_g1" : "k_bucket_acc_g2", k_bucket_acc<F>, (n_keys + 127) / 128, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy);
+    {
+        static const int occ = [] { const char* v = getenv("OG_ACC_OCC"); return v ? atoi(v) : 0; }();
+        const char* kn = sizeof(F) == 32 ? "k_bucket_acc_g1" : "k_bucket_acc_g2";
+        unsigned grid = (n_keys + 127) / 128;
+        if constexpr (sizeof(F) == 32) {
+            if (occ == 4) { auto k = k_bucket_acc<F, 4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
+            else if (occ == 6) { auto k = k_bucket_acc<F, 6>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
+            else { auto k = k_bucket_acc<F, 5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
+        } else {
+            if (occ == 3) { auto k = k_bucket_acc<F, 3>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
+            else { auto k = k_bucket_acc<F, 2>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
+        }
+    }
     auto k_heavy = k_bucket_heavy<F, HT>;
     OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_bucket_heavy_g1" : "k_bucket_heavy_g2", k_heavy, ctx->sm_count, HT, HT * sizeof(XYZZ<F>), d_table, d_sorted, d_offsets, d_counts, d_buckets, d_heavy);
     // reduction levels
