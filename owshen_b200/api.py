@@ -135,11 +135,15 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().og_free(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.og_free(self._h)
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown
+            pass
 
     def sync(self):
         _check(lib().og_sync(self._h), self)
@@ -304,11 +308,15 @@ class ProvingKey:
         self.n_vars, self.n_pub, self.log_m, self.depth = (x.value for x in v)
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().og_free_pk(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None and getattr(self.ctx, "_h", None):
+            _lib.og_free_pk(self._h)
+        self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def h_evals(self, witness: bytes) -> bytes:
         out = C.create_string_buffer(32 << self.log_m)

@@ -305,13 +305,15 @@ __global__ void __launch_bounds__(64) k_group_total(const XYZZ<F>* __restrict__ 
 
 template <class F>
 static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
-                           const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, XYZZ<F>* d_buckets, XYZZ<F>* d_lvl,
-                           uint32_t* d_heavy, XYZZ<F>* d_totals) {
+                           const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, uint64_t n_entries_max, XYZZ<F>* d_buckets,
+                           XYZZ<F>* d_lvl, uint32_t* d_heavy, XYZZ<F>* d_totals) {
     uint32_t n_keys = n_groups * nb;
     constexpr int HT = sizeof(F) == 32 ? 256 : 128;
     OG_CUDA(ctx, cudaMemsetAsync(d_heavy, 0, sizeof(uint32_t), ctx->stream));
-    // cap: a bucket that would keep one thread busy far longer than its warp-mates goes to a CTA
-    uint32_t cap = 4096;
+    // cap: a bucket that would keep one thread busy far longer than the average goes to a whole CTA
+    // (skewed scalars: witness 0/1 values, short scalars whose top window has few distinct digits)
+    uint64_t avg = n_entries_max / (n_keys ? n_keys : 1);
+    uint32_t cap = (uint32_t)(4 * avg < 128 ? 128 : 4 * avg);
     {
         static const int occ = [] { const char* v = getenv("OG_ACC_OCC"); return v ? atoi(v) : 0; }();
         const char* kn = sizeof(F) == 32 ? "k_bucket_acc_g1" : "k_bucket_acc_g2";
@@ -350,17 +352,17 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
 
 #ifdef OG_MSM_G1
 int32_t msm_buckets_g1(og_ctx* ctx, const G1Affine* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
-                       const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, G1XYZZ* d_buckets, G1XYZZ* d_lvl,
-                       uint32_t* d_heavy, G1XYZZ* d_totals) {
-    return msm_buckets<Fq>(ctx, d_table, d_sorted, d_offsets, d_counts, n_groups, nb, d_buckets, d_lvl, d_heavy, d_totals);
+                       const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, uint64_t n_entries_max, G1XYZZ* d_buckets,
+                       G1XYZZ* d_lvl, uint32_t* d_heavy, G1XYZZ* d_totals) {
+    return msm_buckets<Fq>(ctx, d_table, d_sorted, d_offsets, d_counts, n_groups, nb, n_entries_max, d_buckets, d_lvl, d_heavy, d_totals);
 }
 #endif  // OG_MSM_G1
 
 #ifdef OG_MSM_G2
 int32_t msm_buckets_g2(og_ctx* ctx, const G2Affine* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
-                       const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, G2XYZZ* d_buckets, G2XYZZ* d_lvl,
-                       uint32_t* d_heavy, G2XYZZ* d_totals) {
-    return msm_buckets<Fq2>(ctx, d_table, d_sorted, d_offsets, d_counts, n_groups, nb, d_buckets, d_lvl, d_heavy, d_totals);
+                       const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, uint64_t n_entries_max, G2XYZZ* d_buckets,
+                       G2XYZZ* d_lvl, uint32_t* d_heavy, G2XYZZ* d_totals) {
+    return msm_buckets<Fq2>(ctx, d_table, d_sorted, d_offsets, d_counts, n_groups, nb, n_entries_max, d_buckets, d_lvl, d_heavy, d_totals);
 }
 #endif  // OG_MSM_G2
 
@@ -415,7 +417,7 @@ static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sc
     plan.key_stride_problem = 0; plan.key_stride_window = 1; plan.tidx_window_stride = 0;
     plan.montgomery = 0;
     OG_TRY(msm_sort_digits(ctx, plan, n_keys, counts, offsets, cursor, sorted));
-    OG_TRY((msm_buckets<F>(ctx, pts, sorted, offsets, counts, W, nb, buckets, lvl, heavy, totals)));
+    OG_TRY((msm_buckets<F>(ctx, pts, sorted, offsets, counts, W, nb, n * W, buckets, lvl, heavy, totals)));
     OG_LAUNCH(ctx, k_horner<F>, 1, 32, 0, totals, W, c, d_out);
     return OG_OK;
 }
