@@ -342,7 +342,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_source": peak_kind,
+                         "frac": achieved / hbm_peak if hbm_peak else None, "frac_of_nominal_8tbs": achieved / 8000.0,
+                         "traffic": traffic, "peak_source": peak_kind,
                          "avg_launch_ms": avg_ms, "launches": kn, "share_of_step": kms / total_prof_ms if total_prof_ms else None,
                          "note": "MSM is bound by the 32-bit integer multiply-add pipe, not HBM (DESIGN.md 5); see `imad`"},
             "imad": {"kernel": kname, "achieved_wide_mad_per_s": wide_rate, "peak_wide_mad_per_s": pipes["imad_wide_carry_chain_per_s"],

@@ -309,7 +309,17 @@ struct Fq2 {
 // Fq2 products are inlined.  Kernels keep ptxas time sane by calling the out-of-line group operations of
 // ec.cuh (xyzz_*_ni) everywhere except in the bucket-accumulation inner loop (a G2 group operation is
 // ~10k instructions; inlining several of them into one kernel once cost 30 minutes of ptxas).
+#if defined(__CUDA_ARCH__) && defined(OG_FP_MUL_CALL)
+// Translation units whose kernels would inline dozens of Fq2 products per group operation keep ONE copy of
+// the Fq2 multiplier / squarer (arguments and result travel in registers): the fully inlined G2 bucket kernel
+// overflowed the instruction cache (ncu: 30 % of warp samples in "no_instructions", profiles/).
+static __device__ __noinline__ Fq2 fq2_mul_call(Fq2 a, Fq2 b) { return Fq2::mul_inl(a, b); }
+static __device__ __noinline__ Fq2 fq2_sqr_call(Fq2 a) { return Fq2::sqr_inl(a); }
+OG_HD Fq2 operator*(const Fq2& a, const Fq2& b) { return fq2_mul_call(a, b); }
+OG_HD Fq2 Fq2::sqr() const { return fq2_sqr_call(*this); }
+#else
 OG_HD Fq2 operator*(const Fq2& a, const Fq2& b) { return Fq2::mul_inl(a, b); }
 OG_HD Fq2 Fq2::sqr() const { return Fq2::sqr_inl(*this); }
+#endif
 
 }  // namespace og

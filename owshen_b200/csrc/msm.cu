@@ -323,8 +323,8 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
             else if (occ == 6) { auto k = k_bucket_acc<F, 6>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
             else { auto k = k_bucket_acc<F, 5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
         } else {
-            if (occ == 3) { auto k = k_bucket_acc<F, 3>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
-            else { auto k = k_bucket_acc<F, 2>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
+            if (occ == 2) { auto k = k_bucket_acc<F, 2>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
+            else { auto k = k_bucket_acc<F, 3>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy); }
         }
     }
     auto k_heavy = k_bucket_heavy<F, HT>;
