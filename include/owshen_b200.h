@@ -91,6 +91,15 @@ int32_t og_mimc7_merkle_paths_dev(og_ctx* ctx, const uint8_t* d_leaves, const ui
  * levels concatenated: sum_{l=0..log2 n} (n >> l) * 32 B */
 int32_t og_mimc7_merkle_build(og_ctx* ctx, const uint8_t* leaves, uint64_t n_leaves_pow2, uint8_t* out_levels);
 
+/* ---- BabyJubJub EdDSA-style batch verification -------------------------------------------
+ * Replaces a loop over PointCompressed::verify, /root/reference/src/blockchain/tx/owshen_airdrop/babyjubjub/
+ * mod.rs:99-115 (with decompress :88-98, multiply :68-78, hash :202-204).  Per signature: pk_x 32 B and one
+ * is_odd byte (PointCompressed, mod.rs:19), message 32 B, signature = R.x || R.y || s (96 B).
+ * hash_kind 0 = the reference's placeholder product hash, 1 = MultiMiMC7 (not reference behaviour).
+ * out_status[i]: 1 verifies, 0 does not, 2 = the reference would return Err (pk does not decompress). */
+int32_t og_bjj_verify_batch(og_ctx* ctx, const uint8_t* pk_x, const uint8_t* pk_is_odd, const uint8_t* messages,
+                            const uint8_t* signatures, uint32_t n, int32_t hash_kind, uint8_t* out_status);
+
 /* ---- MSM (BASELINE configs 3 and 5) ----------------------------------------------------------- */
 int32_t og_msm_g1(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out64);
 int32_t og_msm_g2(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out128);

@@ -53,6 +53,7 @@ _SIGS = {
     "og_mimc7_merkle_paths": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "og_mimc7_merkle_paths_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "og_mimc7_merkle_build": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "og_bjj_verify_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]),
     "og_msm_g1": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_msm_g2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_msm_g1_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
@@ -207,6 +208,14 @@ class Context:
         n = len(leaves) // 32
         out = C.create_string_buffer(32 * (2 * n - 1))
         _check(lib().og_mimc7_merkle_build(self._h, leaves, n, out), self)
+        return out.raw
+
+    def bjj_verify_batch(self, pk_x: bytes, pk_is_odd: bytes, messages: bytes, signatures: bytes, hash_kind: int = 0) -> bytes:
+        """BabyJubJub batch verification; one status byte per signature (1 ok, 0 bad, 2 undecompressible pk)."""
+        n = len(pk_is_odd)
+        assert len(pk_x) == 32 * n and len(messages) == 32 * n and len(signatures) == 96 * n
+        out = C.create_string_buffer(n)
+        _check(lib().og_bjj_verify_batch(self._h, pk_x, pk_is_odd, messages, signatures, n, hash_kind, out), self)
         return out.raw
 
     def msm_g1(self, points: bytes, scalars: bytes) -> bytes:

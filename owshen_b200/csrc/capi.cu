@@ -353,6 +353,23 @@ int32_t og_mimc7_merkle_build(og_ctx* ctx, const uint8_t* leaves, uint64_t n, ui
     return check_flag(ctx);
 }
 
+// ---- BabyJubJub (the reference's own signature scheme, babyjubjub/mod.rs) -----------------------------------
+int32_t og_bjj_verify_batch(og_ctx* ctx, const uint8_t* pk_x, const uint8_t* pk_is_odd, const uint8_t* messages, const uint8_t* signatures,
+                            uint32_t n, int32_t hash_kind, uint8_t* out_status) {
+    if (!ctx || !pk_x || !pk_is_odd || !messages || !signatures || !out_status || hash_kind < 0 || hash_kind > 1) return OG_E_INVALID;
+    if (n == 0) return OG_OK;
+    OG_SLOT(ctx, dx, uint8_t, S_IO_A, 32ull * n);
+    OG_SLOT(ctx, dodd, uint8_t, S_IO_B, n);
+    OG_SLOT(ctx, dm, uint8_t, S_IO_C, 32ull * n);
+    OG_SLOT(ctx, dsg, uint8_t, S_IO_D, 96ull * n);
+    OG_SLOT(ctx, dout, uint8_t, S_IO_E, n);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, dx, pk_x, 32ull * n); H2D(ctx, dodd, pk_is_odd, n); H2D(ctx, dm, messages, 32ull * n); H2D(ctx, dsg, signatures, 96ull * n);
+    OG_TRY(bjj_verify_dev(ctx, dx, dodd, dm, dsg, n, hash_kind, dout));
+    D2H(ctx, out_status, dout, n);
+    return check_flag(ctx);
+}
+
 // ---- MSM --------------------------------------------------------------------------------------------------
 int32_t og_msm_g1_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out64) {
     if (!ctx || !d_out64 || (n && (!d_points || !d_scalars))) return OG_E_INVALID;

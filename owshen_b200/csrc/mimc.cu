@@ -192,3 +192,5 @@ int32_t withdraw_witness_strided_dev(og_ctx* ctx, const WithdrawLayout& L, uint3
 }
 
 }  // namespace og
+
+#include "bjj_impl.cuh"
