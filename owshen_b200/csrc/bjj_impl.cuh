@@ -10,86 +10,12 @@
 // multiplications over Fr in the reference's projective coordinates, compared by cross-multiplication
 // instead of two field inversions.  hash_kind = 1 replaces the placeholder product by MultiMiMC7
 // (not reference behaviour; the "real hash" variant the survey asks for).
+#include "bjj_core.cuh"
+
 namespace og {
 
 __constant__ uint32_t BJJ_BASE_X[8] = {0xbb957051u, 0x2893f3f6u, 0x0534e0b6u, 0x2ab8d801u, 0x9d6277c1u, 0x4eacb2e0u, 0xd63e739bu, 0x0bb77a6au};   // mod.rs:177-183
 __constant__ uint32_t BJJ_BASE_Y[8] = {0x872d7d8bu, 0x4b3c257au, 0xb9e13377u, 0xfce0051fu, 0xd16bf9edu, 0x25572e1cu, 0xf7a0b249u, 0x25797203u};
-
-struct BjjPoint { Fr x, y, z; };     // z == 0: the reference's "empty accumulator" sentinel
-
-__device__ __forceinline__ Fr bjj_a() { return Fr::from_u32(168700); }
-__device__ __forceinline__ Fr bjj_d() { return Fr::from_u32(168696); }
-
-static __device__ __noinline__ void bjj_double(BjjPoint* p, const Fr* A) {
-    if (p->z.is_zero()) return;
-    Fr b = (p->x + p->y).sqr(), c = p->x.sqr(), d = p->y.sqr();
-    Fr e = *A * c, f = e + d, h = p->z.sqr();
-    Fr j = f - h.dbl();
-    p->x = (b - c - d) * j;
-    p->y = f * (e - d);
-    p->z = f * j;
-}
-
-// unified addition (complete on this curve: a is a square, d is not), so the reference's
-// "equal points -> double" branch needs no special case
-static __device__ __noinline__ void bjj_add(BjjPoint* p, const BjjPoint* q, const Fr* A, const Fr* D) {
-    if (p->z.is_zero()) { *p = *q; return; }
-    if (q->z.is_zero()) return;
-    Fr a = p->z * q->z, b = a.sqr(), c = p->x * q->x, d = p->y * q->y;
-    Fr e = *D * c * d, f = b - e, g = b + e;
-    Fr x3 = a * f * ((p->x + p->y) * (q->x + q->y) - c - d);
-    Fr y3 = a * g * (d - *A * c);
-    p->x = x3; p->y = y3; p->z = f * g;
-}
-
-static __device__ __noinline__ void bjj_mul(BjjPoint* out, const BjjPoint* base, const Fr* k, const Fr* A, const Fr* D) {
-    uint32_t s[8];
-    k->to_canonical(s);
-    BjjPoint acc{Fr::zero(), Fr::one(), Fr::zero()};
-    for (int i = 255; i >= 0; i--) {
-        bjj_double(&acc, A);
-        if ((s[i >> 5] >> (i & 31)) & 1) bjj_add(&acc, base, A, D);
-    }
-    *out = acc;
-}
-
-__device__ __forceinline__ bool bjj_on_curve(const Fr& x, const Fr& y, const Fr& A, const Fr& D) {
-    Fr xx = x.sqr(), yy = y.sqr();
-    return yy + A * xx == Fr::one() + D * xx * yy;
-}
-
-// Tonelli-Shanks (r - 1 = 2^28 t, non-residue 7); false if a is a non-residue
-static __device__ __noinline__ bool fr_sqrt(Fr* out, const Fr* a) {
-    if (a->is_zero()) { *out = *a; return true; }
-    // t = (r - 1) >> 28
-    uint32_t e[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) e[i] = FrParams::mod(i);
-    e[0] -= 1;
-    uint32_t t[8];
-    for (int i = 0; i < 8; i++) t[i] = (e[i] >> 28) | (i < 7 ? e[i + 1] << 4 : 0);
-    uint32_t half[8];                                  // (t + 1) / 2 ; t is odd
-    {
-        uint32_t c = 1;
-        for (int i = 0; i < 8; i++) { uint32_t v = t[i] + c; c = (v < c) ? 1 : 0; half[i] = v; }
-        for (int i = 0; i < 8; i++) half[i] = (half[i] >> 1) | (i < 7 ? half[i + 1] << 31 : 0);
-    }
-    Fr z = Fr::from_u32(7).pow(t);
-    Fr x = a->pow(half), b = a->pow(t);
-    uint32_t m = 28;
-    while (b != Fr::one()) {
-        uint32_t i = 0;
-        Fr b2 = b;
-        while (b2 != Fr::one()) { b2 = b2.sqr(); i++; if (i == m) return false; }
-        Fr w = z;
-        for (uint32_t k = 0; k + i + 1 < m; k++) w = w.sqr();
-        x = x * w; z = w.sqr(); b = b * z; m = i;
-    }
-    *out = x;
-    return true;
-}
-
-__device__ __forceinline__ bool fr_is_odd(const Fr& v) { uint32_t c[8]; v.to_canonical(c); return c[0] & 1; }
 
 static __device__ __noinline__ Fr mimc7_multi_hash5(const Fr* in) {     // MultiMiMC7(in[0..5), key 0)
     Fr r = Fr::zero();
@@ -103,36 +29,18 @@ __global__ void __launch_bounds__(64) k_bjj_verify(const uint8_t* __restrict__ p
                                                    int hash_kind, uint8_t* __restrict__ out, int* flag) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Fr A = bjj_a(), D = bjj_d(), one = Fr::one();
     Fr x = load_canonical<Fr>(pk_x + 32ull * i, flag);
     Fr msg = load_canonical<Fr>(msgs + 32ull * i, flag);
     Fr rx = load_canonical<Fr>(sigs + 96ull * i, flag), ry = load_canonical<Fr>(sigs + 96ull * i + 32, flag);
     Fr s = load_canonical<Fr>(sigs + 96ull * i + 64, flag);
-    // decompress (mod.rs:88-98)
-    Fr xx = x.sqr();
-    Fr den = one - D * xx;
-    if (den.is_zero()) { out[i] = 2; return; }
-    Fr y2 = den.inv() * (one - A * xx), y;
-    if (!fr_sqrt(&y, &y2)) { out[i] = 2; return; }
-    if (fr_is_odd(y) != (pk_odd[i] != 0)) y = y.neg();
-    // verify (mod.rs:99-115)
-    if (!bjj_on_curve(x, y, A, D) || !bjj_on_curve(rx, ry, A, D)) { out[i] = 0; return; }
-    Fr h;
-    if (hash_kind == 0) h = rx * ry * x * y * msg;       // placeholder product, mod.rs:202-204
-    else { Fr in[5] = {rx, ry, x, y, msg}; h = mimc7_multi_hash5(in); }
     uint32_t bxc[8], byc[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) { bxc[k] = BJJ_BASE_X[k]; byc[k] = BJJ_BASE_Y[k]; }
     const Fr bx = Fr::from_canonical(bxc), by = Fr::from_canonical(byc);
-    BjjPoint base{bx, by, one}, pk{x, y, one}, rr{rx, ry, one}, sb, ha;
-    bjj_mul(&sb, &base, &s, &A, &D);
-    bjj_mul(&ha, &pk, &h, &A, &D);
-    bjj_add(&ha, &rr, &A, &D);
-    // affine equality by cross-multiplication; an empty accumulator is the affine point (0, 1)
-    if (sb.z.is_zero()) sb = BjjPoint{Fr::zero(), one, one};
-    if (ha.z.is_zero()) ha = BjjPoint{Fr::zero(), one, one};
-    bool eq = (sb.x * ha.z == ha.x * sb.z) && (sb.y * ha.z == ha.y * sb.z);
-    out[i] = eq ? 1 : 0;
+    out[i] = bjj_verify_one(x, pk_odd[i] != 0, msg, rx, ry, s, bx, by, [hash_kind](const Fr* in) {
+        if (hash_kind == 0) return in[0] * in[1] * in[2] * in[3] * in[4];     // placeholder product, mod.rs:202-204
+        return mimc7_multi_hash5(in);
+    });
 }
 
 int32_t bjj_verify_dev(og_ctx* ctx, const uint8_t* d_pk_x, const uint8_t* d_pk_odd, const uint8_t* d_msgs, const uint8_t* d_sigs,

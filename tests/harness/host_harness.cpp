@@ -53,3 +53,15 @@ void ht_g2_sum(const uint8_t* pts, uint64_t n, int mode, uint8_t* out) {
     storeg2(out, acc.to_affine());
 }
 }
+
+// ---- BabyJubJub verification core (bjj_core.cuh) on the host, placeholder-product hash -------------------
+#include "bjj_core.cuh"
+extern "C" void ht_bjj_verify(const uint8_t* pk_x, const uint8_t* pk_odd, const uint8_t* msgs, const uint8_t* sigs, uint32_t n,
+                              const uint8_t* base_xy, uint8_t* out) {
+    Fr bx = load<Fr>(base_xy), by = load<Fr>(base_xy + 32);
+    for (uint32_t i = 0; i < n; i++) {
+        out[i] = bjj_verify_one(load<Fr>(pk_x + 32 * i), pk_odd[i] != 0, load<Fr>(msgs + 32 * i), load<Fr>(sigs + 96 * i),
+                                load<Fr>(sigs + 96 * i + 32), load<Fr>(sigs + 96 * i + 64), bx, by,
+                                [](const Fr* in) { return in[0] * in[1] * in[2] * in[3] * in[4]; });
+    }
+}

@@ -91,4 +91,4 @@ def test_gpu_batch_verify_matches_oracle(ctx, hash_kind):
     pk = bjj.to_pub(12345)
     assert list(ctx.bjj_verify_batch(*_pack([pk, pk], [123456, 123457], [sig, sig]))) == [1, 0]
     # undecompressible public key -> status 2 (the reference returns Err)
-    assert list(ctx.bjj_verify_batch(*_pack([(2, 0)], [1], [sig]))) == [2]
+    assert list(ctx.bjj_verify_batch(*_pack([(3, 0)], [1], [sig]))) == [2]

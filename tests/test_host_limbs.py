@@ -80,3 +80,15 @@ def test_group_formulas_with_exceptional_cases(h):
         o = C.create_string_buffer(128)
         h.ht_g2_sum(b"".join(map(bn.g2_to_bytes, pts2)), C.c_uint64(len(pts2)), mode, o)
         assert o.raw == bn.g2_to_bytes(exp)
+
+
+def test_babyjubjub_verification_core_on_host(h):
+    """bjj_core.cuh (the code the GPU kernel runs) against the oracle's restatement of the reference."""
+    from oracle import babyjubjub as bjj
+    from tests.test_babyjubjub import _cases, _pack
+    rng = random.Random(5)
+    pks, msgs, sigs, expect = _cases(rng, 16, 0)
+    pkx, odd, m, s = _pack(pks + [(3, 0)], msgs + [1], sigs + [sigs[0]])
+    out = C.create_string_buffer(len(odd))
+    h.ht_bjj_verify(pkx, odd, m, s, len(odd), bn.fr_to_bytes(bjj.BASE[0]) + bn.fr_to_bytes(bjj.BASE[1]), out)
+    assert list(out.raw) == [1 if e else 0 for e in expect] + [2]
