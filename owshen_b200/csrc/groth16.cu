@@ -364,7 +364,7 @@ static int32_t run_msm_g1(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t B
     plan.montgomery = 1;
     uint32_t n_keys = B * pk->nb;
     OG_TRY(msm_sort_digits(ctx, plan, n_keys, b.counts, b.offsets, b.cursor, b.sorted));
-    return msm_buckets_g1(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb, (uint64_t)B * n_pts * pk->n_windows, b.bk1, b.lvl1, b.heavy, totals);
+    return msm_buckets_g1(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb, (uint64_t)B * n_pts * pk->n_windows, b.bk1, b.lvl1, b.heavy, b.cursor, totals);
 }
 static int32_t run_msm_g2(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t B, const G2Affine* table, uint32_t n_pts,
                           const Fr* scalars, uint32_t stride, G2XYZZ* totals) {
@@ -376,7 +376,7 @@ static int32_t run_msm_g2(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t B
     plan.montgomery = 1;
     uint32_t n_keys = B * pk->nb;
     OG_TRY(msm_sort_digits(ctx, plan, n_keys, b.counts, b.offsets, b.cursor, b.sorted));
-    return msm_buckets_g2(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb, (uint64_t)B * n_pts * pk->n_windows, b.bk2, b.lvl2, b.heavy, totals);
+    return msm_buckets_g2(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb, (uint64_t)B * n_pts * pk->n_windows, b.bk2, b.lvl2, b.heavy, b.cursor, totals);
 }
 
 // proofs [off, off+B): everything between the witness rows (already in b.W) and the per-proof MSM totals

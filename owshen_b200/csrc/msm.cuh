@@ -32,13 +32,13 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
 // Accumulate every bucket and reduce each group to sum_b (b+1) * bucket_b.
 // d_buckets: n_groups * nb XYZZ scratch; d_lvl: msm_lvl_elems(n_groups, nb) XYZZ scratch;
 // d_heavy: n_keys + 1 u32 scratch; n_entries_max: upper bound on the sorted entries (sets the heavy-bucket cap);
-// result: d_totals[n_groups].
+// d_perm: n_keys u32 scratch (the sort's cursor array may be reused); result: d_totals[n_groups].
 int32_t msm_buckets_g1(og_ctx* ctx, const G1Affine* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
                        const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, uint64_t n_entries_max, G1XYZZ* d_buckets,
-                       G1XYZZ* d_lvl, uint32_t* d_heavy, G1XYZZ* d_totals);
+                       G1XYZZ* d_lvl, uint32_t* d_heavy, uint32_t* d_perm, G1XYZZ* d_totals);
 int32_t msm_buckets_g2(og_ctx* ctx, const G2Affine* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
                        const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, uint64_t n_entries_max, G2XYZZ* d_buckets,
-                       G2XYZZ* d_lvl, uint32_t* d_heavy, G2XYZZ* d_totals);
+                       G2XYZZ* d_lvl, uint32_t* d_heavy, uint32_t* d_perm, G2XYZZ* d_totals);
 static inline size_t msm_lvl_elems(uint32_t n_groups, uint32_t nb) { return 4 * ((size_t)n_groups * ((nb + 31) / 32) + 16); }
 
 // one-shot MSMs on device buffers holding boundary bytes (affine points, canonical scalars)
