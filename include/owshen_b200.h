@@ -69,6 +69,9 @@ int32_t og_imad_peak(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s);
  * a Montgomery row, IMAD.WIDE.U32.X): the honest roofline denominator of the field multiplier */
 int32_t og_int_pipe_peaks(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s, double* carry_chain_wide_per_s);
 
+/* FP64 fused multiply-adds per second (planning probe: the FP64 pipe is idle in every kernel of this library) */
+int32_t og_fp64_peak(og_ctx* ctx, double* dfma_per_s);
+
 /* ---- element-wise field ops (parity probes for the limb arithmetic) ------------------------- */
 /* field: 0 = Fq, 1 = Fr; op: 0 = mul, 1 = add, 2 = sub */
 int32_t og_field_op(og_ctx* ctx, int32_t field, int32_t op, const uint8_t* a, const uint8_t* b,

@@ -241,9 +241,45 @@ __global__ void __launch_bounds__(256) k_imad(uint32_t* out, uint32_t iters, uin
         if (s == 0x1234567u) out[0] = s;
     }
 }
+// FP64 pipe probe (round-2 planning: DFMA-based 52-bit-limb products would run beside the integer pipe)
+__global__ void __launch_bounds__(256) k_dfma(double* out, uint32_t iters, double seed) {
+    double w[8], x = 1.0000001 + seed * 1e-9, y = 0.9999999;
+#pragma unroll
+    for (int k = 0; k < 8; k++) w[k] = threadIdx.x * 0.001 + k + seed;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) w[k] = __fma_rz(w[k], x, y);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += w[k];
+    if (s == 1.2345) out[0] = s;
+}
+
 }  // namespace og
 
 extern "C" {
+
+int32_t og_fp64_peak(og_ctx* ctx, double* dfma_per_s) {
+    if (!ctx || !dfma_per_s) return OG_E_INVALID;
+    OG_SLOT(ctx, d_out, double, S_IO_A, 64);
+    const uint32_t iters = 2048, ctas = ctx->sm_count * 8, threads = 256;
+    float ms = 0;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        OG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        OG_LAUNCH(ctx, k_dfma, ctas, threads, 0, d_out, iters, (double)rep);
+        OG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        OG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        OG_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        double rate = (double)ctas * threads * iters * 64.0 / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    *dfma_per_s = best;
+    return OG_OK;
+}
 
 int32_t og_imad_peak(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s) {
     if (!ctx || !mad_per_s || !wide_mad_per_s) return OG_E_INVALID;

@@ -124,6 +124,82 @@ __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restric
     }
 }
 
+// Tiled variant for groups with nb <= 4096 buckets (the batched prover: one group per proof).  A CTA owns a
+// tile of one problem's scalars, histograms its digits in shared memory and touches global memory once per
+// bucket instead of once per digit (5-20x fewer global atomics); in the scatter pass it reserves a contiguous
+// run per bucket, so the 4-byte entries of a tile land in runs instead of isolated sectors.
+constexpr uint32_t DIG_TILE = 4096, DIG_THREADS = 256, DIG_MAX_NB = 4096;
+
+struct DigitIter {
+    uint32_t s[9];
+    __device__ __forceinline__ bool load(const DigitPlan& P, uint32_t prob, uint64_t i, int* flag) {
+        const uint32_t* sp = P.scalars + ((uint64_t)prob * P.scalar_stride + i) * 8;
+        if (P.montgomery) {
+            Fr v;
+#pragma unroll
+            for (int j = 0; j < 8; j++) v.l[j] = sp[j];
+            v.to_canonical(s);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) s[j] = sp[j];
+            if (!Fr::canonical_lt_mod(s)) { atomicOr(flag, 1); return false; }
+        }
+        s[8] = 0;
+        return (s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) != 0;
+    }
+    // calls f(window, magnitude - 1, negative) for every non-zero signed digit
+    template <class Fn>
+    __device__ __forceinline__ void for_each(const DigitPlan& P, Fn f) const {
+        const uint32_t c = P.c, half = 1u << (c - 1), mask = (1u << c) - 1;
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < P.n_windows; w++) {
+            uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
+            uint64_t two = ((uint64_t)s[word + 1] << 32) | s[word];
+            uint32_t v = ((uint32_t)(two >> sh) & mask) + carry;
+            uint32_t neg = v > half;
+            uint32_t mag = neg ? (1u << c) - v : v;
+            carry = neg;
+            if (mag) f(w, mag - 1, neg);
+        }
+    }
+};
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(DIG_THREADS) k_digits_tiled(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
+    __shared__ uint32_t hist[DIG_MAX_NB];
+    __shared__ uint32_t base[SCATTER ? DIG_MAX_NB : 1];
+    const uint32_t prob = blockIdx.y, nb = P.nb;
+    const uint64_t lo = (uint64_t)blockIdx.x * DIG_TILE;
+    const uint64_t hi = lo + DIG_TILE < P.n ? lo + DIG_TILE : P.n;
+    const uint32_t key0 = prob * P.key_stride_problem * nb;          // key_stride_window == 0 in this mode
+    for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) hist[b] = 0;
+    __syncthreads();
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += DIG_THREADS) {
+        DigitIter it;
+        if (it.load(P, prob, i, flag)) it.for_each(P, [&](uint32_t, uint32_t b, uint32_t) { atomicAdd(&hist[b], 1u); });
+    }
+    __syncthreads();
+    if (!SCATTER) {
+        for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) if (hist[b]) atomicAdd(&counts[key0 + b], hist[b]);
+        return;
+    }
+    for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) {
+        uint32_t h = hist[b];
+        base[b] = h ? offsets[key0 + b] + atomicAdd(&cursor[key0 + b], h) : 0;
+        hist[b] = 0;                                                  // reused as the running rank inside the run
+    }
+    __syncthreads();
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += DIG_THREADS) {
+        DigitIter it;
+        if (it.load(P, prob, i, flag))
+            it.for_each(P, [&](uint32_t w, uint32_t b, uint32_t neg) {
+                uint32_t pos = base[b] + atomicAdd(&hist[b], 1u);
+                sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
+            });
+    }
+}
+
 // ---- 2: exclusive scan: tile sums -> scan of the tile sums (one CTA) -> tile rescan with offsets ----------
 constexpr uint32_t SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
 
@@ -190,8 +266,11 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
         OG_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * ((size_t)n_keys + 1), ctx->stream));
         return OG_OK;
     }
+    const bool tiled = plan.key_stride_window == 0 && plan.nb <= DIG_MAX_NB;
     dim3 grid((unsigned)((plan.n + 255) / 256), plan.n_problems);
-    OG_LAUNCH(ctx, k_digits<false>, grid, 256, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
+    dim3 tgrid((unsigned)((plan.n + DIG_TILE - 1) / DIG_TILE), plan.n_problems);
+    if (tiled) OG_LAUNCHN(ctx, "k_digits_tiled<count>", k_digits_tiled<false>, tgrid, DIG_THREADS, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
+    else OG_LAUNCH(ctx, k_digits<false>, grid, 256, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
     {   // offsets[n_keys] receives the grand total; the tile sums live in the cursor array (zeroed again below)
         uint32_t n_tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
         OG_SLOT(ctx, tile_sums, uint32_t, S_MSM_MISC, 4 * (size_t)n_tiles);
@@ -199,7 +278,11 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
         OG_LAUNCH(ctx, k_scan_tile_sums, 1, SCAN_THREADS, 0, tile_sums, n_tiles, d_offsets + n_keys);
         OG_LAUNCH(ctx, k_scan_apply, n_tiles, SCAN_THREADS, 0, d_counts, n_keys, tile_sums, d_offsets);
     }
-    OG_LAUNCH(ctx, k_digits<true>, grid, 256, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
+    // measured: the tiled scatter (run reservation + shared-memory ranks) is slower than the plain one
+    // (39 vs 33 ms per 1024 proofs) while the tiled count is 5x faster (5 vs 24 ms) -> tiled count, plain scatter
+    static const int tiled_scatter = [] { const char* v = getenv("OG_TILED_SCATTER"); return v ? atoi(v) : 0; }();
+    if (tiled && tiled_scatter) OG_LAUNCHN(ctx, "k_digits_tiled<scatter>", k_digits_tiled<true>, tgrid, DIG_THREADS, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
+    else OG_LAUNCH(ctx, k_digits<true>, grid, 256, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
     return OG_OK;
 }
 #endif  // OG_MSM_G1
@@ -300,7 +383,8 @@ __global__ void __launch_bounds__(THREADS) k_bucket_heavy(const Affine<F>* __res
     }
 }
 
-// ---- 5: weighted reduction, 32 children per parent -------------------------------------------------------
+constexpr uint32_t RED_FAN_LOG2 = 3, RED_FAN = 1u << RED_FAN_LOG2;   // 8 children per parent: more threads, shorter chains
+// ---- 5: weighted reduction, RED_FAN children per parent -------------------------------------------------------
 // Element e of a level carries S_e (plain sum of the buckets under e) and U_e (their 0-based weighted sum
 // relative to e's first bucket).  Merging children c_0..c_k, each covering 2^w_log2 buckets:
 //   S_p = sum S_c;   U_p = sum U_c + 2^w_log2 * sum_c idx(c) * S_c   (running-sum trick for the last term).
@@ -313,7 +397,7 @@ __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__
     uint32_t g = t / n_out, p = t % n_out;
     const XYZZ<F>* S = S_in + (size_t)g * n_in;
     const XYZZ<F>* U = U_in ? U_in + (size_t)g * n_in : nullptr;
-    uint32_t lo = p * 32, hi = min(n_in, lo + 32);
+    uint32_t lo = p * RED_FAN, hi = min(n_in, lo + RED_FAN);
     XYZZ<F> R = XYZZ<F>::inf(), T = XYZZ<F>::inf(), Us = XYZZ<F>::inf();
     for (uint32_t i = hi - 1; i > lo; i--) {
         xyzz_add_ni(&R, &S[i]);
@@ -367,7 +451,7 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     auto k_heavy = k_bucket_heavy<F, HT>;
     OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_bucket_heavy_g1" : "k_bucket_heavy_g2", k_heavy, ctx->sm_count, HT, HT * sizeof(XYZZ<F>), d_table, d_sorted, d_offsets, d_counts, d_buckets, d_heavy);
     // reduction levels
-    size_t lvl_stride = (size_t)n_groups * ((nb + 31) / 32) + 16;
+    size_t lvl_stride = (size_t)n_groups * ((nb + RED_FAN - 1) / RED_FAN) + 16;
     XYZZ<F>* bufS[2] = {d_lvl, d_lvl + lvl_stride};
     XYZZ<F>* bufU[2] = {d_lvl + 2 * lvl_stride, d_lvl + 3 * lvl_stride};
     const XYZZ<F>* S_in = d_buckets;
@@ -375,13 +459,13 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     uint32_t n_in = nb, w_log2 = 0;
     int pp = 0;
     do {
-        uint32_t n_out = (n_in + 31) / 32;
+        uint32_t n_out = (n_in + RED_FAN - 1) / RED_FAN;
         uint32_t threads = n_groups * n_out;
         OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2", k_reduce_level<F>, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]);
         S_in = bufS[pp]; U_in = bufU[pp];
         pp ^= 1;
         n_in = n_out;
-        w_log2 += 5;
+        w_log2 += RED_FAN_LOG2;
     } while (n_in > 1);
     OG_LAUNCH(ctx, k_group_total<F>, (n_groups + 63) / 64, 64, 0, S_in, U_in, n_groups, d_totals);
     return OG_OK;
@@ -443,7 +527,7 @@ static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sc
     OG_SLOT(ctx, cursor, uint32_t, S_MSM_CURSOR, 4 * (size_t)n_keys);
     OG_SLOT(ctx, sorted, uint32_t, S_MSM_SORTED, 4 * (size_t)n * W);
     OG_SLOT(ctx, buckets, XYZZ<F>, S_MSM_BUCKETS, sizeof(XYZZ<F>) * (size_t)n_keys);
-    OG_SLOT(ctx, lvl, XYZZ<F>, S_MSM_SEG, sizeof(XYZZ<F>) * 4 * ((size_t)W * ((nb + 31) / 32) + 16));
+    OG_SLOT(ctx, lvl, XYZZ<F>, S_MSM_SEG, sizeof(XYZZ<F>) * msm_lvl_elems(W, nb));
     OG_SLOT(ctx, heavy, uint32_t, S_MSM_HEAVY, 4 * ((size_t)n_keys + 1));
     OG_SLOT(ctx, totals, XYZZ<F>, S_MSM_OUT, sizeof(XYZZ<F>) * W);
     OG_LAUNCH(ctx, k_points_to_mont<F>, (unsigned)((n + 127) / 128), 128, 0, d_points, n, pts, ctx->d_flag);

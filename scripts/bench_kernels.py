@@ -69,6 +69,7 @@ def main():
     peak, peak_src = hbm_peak()
     pipes = ctx.int_pipe_peaks()
     print(json.dumps({"kernel": "int_pipe_peaks", **pipes, "note": "multiply-adds per second; carry-chain figure is the Montgomery-row shape"}), flush=True)
+    print(json.dumps({"kernel": "fp64_peak", "dfma_per_s": ctx.fp64_peak(), "note": "FP64 pipe is idle in every kernel of this library (planning probe)"}), flush=True)
     wide_peak = pipes["imad_wide_carry_chain_per_s"]
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device=device)    # 256 MB > L2
 
@@ -135,6 +136,16 @@ def main():
                    flush if n * batch * 32 < (200 << 20) else None)
         line(f"ntt_2^{log_n}_x{batch} (bytes in/out incl. Montgomery conversion kernels)", ms, 64 * n * batch, int(n * batch * (log_n / 2 + 2)),
              {"elements_per_s": n * batch / (ms * 1e-3), "note": "butterfly muls n/2*log n + 2 conversions"})
+    # ---- BabyJubJub batch verification --------------------------------------------
+    n = 1 << 16
+    rb = rng.randbytes
+    pkx = fr_bytes(rng, n); odd = bytes(n); msg = fr_bytes(rng, n); sg = fr_bytes(rng, 3 * n)
+    import time
+    ctx.bjj_verify_batch(pkx[:32 * 64], odd[:64], msg[:32 * 64], sg[:96 * 64])
+    t0 = time.perf_counter(); st = ctx.bjj_verify_batch(pkx, odd, msg, sg); dt = time.perf_counter() - t0
+    print(json.dumps({"kernel": "bjj_verify_batch_65536 (random inputs: ~half fail at decompress, the rest run both scalar multiplications)",
+                      "ms_host_wall_incl_copies": dt * 1e3, "signatures_per_s": n / dt,
+                      "status_histogram": {str(k): st.count(bytes([k])) for k in (0, 1, 2)}}), flush=True)
     ctx.close()
 
 
