@@ -69,6 +69,9 @@ int32_t og_imad_peak(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s);
  * a Montgomery row, IMAD.WIDE.U32.X): the honest roofline denominator of the field multiplier */
 int32_t og_int_pipe_peaks(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s, double* carry_chain_wide_per_s);
 
+/* SM cycles per dependent Fr multiply(+add) for one warp alone on a scheduler, and per iteration of two
+ * independent chains: the latency that bounds the sequential MiMC chains (planning probe) */
+int32_t og_mul_latency(og_ctx* ctx, double* cycles_dependent, double* cycles_two_chains);
 /* FP64 fused multiply-adds per second (planning probe: the FP64 pipe is idle in every kernel of this library) */
 int32_t og_fp64_peak(og_ctx* ctx, double* dfma_per_s);
 

@@ -47,6 +47,7 @@ _SIGS = {
     "og_profile_dump": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_uint64]),
     "og_imad_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "og_int_pipe_peaks": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "og_mul_latency": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "og_fp64_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     "og_field_op": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_mimc7_constants": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
@@ -178,6 +179,11 @@ class Context:
     def imad_peak(self):
         a, b = C.c_double(), C.c_double()
         _check(lib().og_imad_peak(self._h, C.byref(a), C.byref(b)), self)
+        return a.value, b.value
+
+    def mul_latency(self):
+        a, b = C.c_double(), C.c_double()
+        _check(lib().og_mul_latency(self._h, C.byref(a), C.byref(b)), self)
         return a.value, b.value
 
     def fp64_peak(self) -> float:

@@ -241,6 +241,21 @@ __global__ void __launch_bounds__(256) k_imad(uint32_t* out, uint32_t iters, uin
         if (s == 0x1234567u) out[0] = s;
     }
 }
+// latency probe: cycles per DEPENDENT Montgomery multiplication for one warp alone on its scheduler
+// (the MiMC chains are exactly this), and with two independent chains interleaved
+template <int CHAINS>
+__global__ void __launch_bounds__(32) k_mul_latency(Fr* io, uint32_t iters, long long* cycles) {
+    Fr x = io[threadIdx.x], y = io[32 + threadIdx.x], k = io[64 + threadIdx.x];
+    long long t0 = clock64();
+    for (uint32_t i = 0; i < iters; i++) {
+        x = x * x + k;
+        if (CHAINS == 2) y = y * y + k;
+    }
+    long long t1 = clock64();
+    io[threadIdx.x] = x + y;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cycles[0] = (t1 - t0);
+}
+
 // FP64 pipe probe (round-2 planning: DFMA-based 52-bit-limb products would run beside the integer pipe)
 __global__ void __launch_bounds__(256) k_dfma(double* out, uint32_t iters, double seed) {
     double w[8], x = 1.0000001 + seed * 1e-9, y = 0.9999999;
@@ -261,6 +276,24 @@ __global__ void __launch_bounds__(256) k_dfma(double* out, uint32_t iters, doubl
 }  // namespace og
 
 extern "C" {
+
+int32_t og_mul_latency(og_ctx* ctx, double* cycles_dependent, double* cycles_two_chains) {
+    if (!ctx || !cycles_dependent || !cycles_two_chains) return OG_E_INVALID;
+    OG_SLOT(ctx, io, Fr, S_IO_A, sizeof(Fr) * 96 + 64);
+    long long* d_cyc = reinterpret_cast<long long*>(io + 96);
+    OG_CUDA(ctx, cudaMemsetAsync(io, 1, sizeof(Fr) * 96, ctx->stream));
+    const uint32_t iters = 20000;
+    long long h = 0;
+    OG_LAUNCH(ctx, k_mul_latency<1>, 1, 32, 0, io, iters, d_cyc);
+    OG_CUDA(ctx, cudaMemcpyAsync(&h, d_cyc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *cycles_dependent = (double)h / iters;
+    OG_LAUNCH(ctx, k_mul_latency<2>, 1, 32, 0, io, iters, d_cyc);
+    OG_CUDA(ctx, cudaMemcpyAsync(&h, d_cyc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *cycles_two_chains = (double)h / iters;
+    return OG_OK;
+}
 
 int32_t og_fp64_peak(og_ctx* ctx, double* dfma_per_s) {
     if (!ctx || !dfma_per_s) return OG_E_INVALID;

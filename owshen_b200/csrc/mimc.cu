@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "host_math.hpp"
 #include "mimc.cuh"
+#include <stdlib.h>
 
 namespace og {
 
@@ -157,7 +158,8 @@ int32_t mimc_hash2_dev(og_ctx* ctx, const uint8_t* d_l, const uint8_t* d_r, uint
 int32_t mimc_merkle_paths_dev(og_ctx* ctx, const uint8_t* d_leaves, const uint8_t* d_siblings, const uint32_t* d_bits,
                               uint32_t n_paths, uint32_t depth, uint8_t* d_out) {
     if (n_paths == 0) return OG_OK;
-    OG_LAUNCH(ctx, k_merkle_paths, (n_paths + 31) / 32, 32, 0, d_leaves, d_siblings, d_bits, n_paths, depth, d_out, ctx->d_flag);
+    static const unsigned lanes = [] { const char* v = getenv("OG_MIMC_LANES"); int x = v ? atoi(v) : 32; return (unsigned)(x >= 1 && x <= 32 ? x : 32); }();
+    OG_LAUNCH(ctx, k_merkle_paths, (n_paths + lanes - 1) / lanes, lanes, 0, d_leaves, d_siblings, d_bits, n_paths, depth, d_out, ctx->d_flag);
     return OG_OK;
 }
 
