@@ -120,6 +120,19 @@ def parse_pk_blob(pk: bytes, n_vars, n_pub, log_m):
     return out
 
 
+def physical_cores():
+    """Host threads the CPU prover should use: physical cores (SMT siblings slow this integer-bound code down:
+    6.4 proofs/s on 128 threads vs 8.8 on 64 on the round-1 box)."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def cpu_prover_rate(pkb, n_proofs, rng, threads=None):
     """proofs/s of the oracle's C prover on `n_proofs` synthetic witnesses, one proof per host thread."""
     from oracle import cport
@@ -148,6 +161,7 @@ def run_reference(args):
     rng = random.Random(TOXIC_SEED)
     cs = wc.build_r1cs(DEPTH)
     pkb, _ = cport.setup_bytes(cs, *toxic(rng))
+    cport.lib().oc_set_num_threads(physical_cores())
     cores = cport.lib().oc_num_threads()
     sample = max(cores, 8)
     nul, sec, rec, sib, bits, rs = synth_inputs(random.Random(1), sample, DEPTH)
@@ -316,10 +330,11 @@ def main():
         wide_mads = pairs_per_proof_g1 * windows * batch * args.steps * 10 * 128
         wide_rate = wide_mads / (kms * 1e-3) if kms > 0 else 0.0
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             try:
                 from oracle import cport
                 pkb = parse_pk_blob(pk_bytes, info["n_vars"], info["n_pub"], info["log_m"])
+                cport.lib().oc_set_num_threads(physical_cores())
                 cores = cport.lib().oc_num_threads()
                 n_cpu = max(2 * cores, 16) if cores <= 64 else cores
                 rate, cores, dt = cpu_prover_rate(pkb, n_cpu, random.Random(7))

@@ -172,6 +172,16 @@ def test_msm_edge_cases(ctx):
     assert ctx.g2_sum(s5) == exp
 
 
+def test_generator_mul_and_probes(ctx):
+    rng = random.Random(21)
+    ks = cport.frs([0, 1, R - 1] + [rng.randrange(R) for _ in range(30)])
+    assert ctx.g1_generator_mul(ks) == cport.g1_fixed_mul_batch(bn.g1_to_bytes(bn.G1_GEN), ks)
+    assert ctx.g2_generator_mul(ks) == cport.g2_fixed_mul_batch(bn.g2_to_bytes(bn.G2_GEN), ks)
+    p = ctx.int_pipe_peaks()
+    assert p["imad_per_s"] > p["imad_wide_carry_chain_per_s"] > 1e12
+    assert ctx.fp64_peak() > 1e12
+
+
 def test_msm_config3_2_20(ctx):
     """BASELINE config 3: 2^20-point G1 MSM, uniform and witness-like scalars, bit-exact vs the CPU MSM;
     plus linearity msm(P, a) + msm(P, b) == msm(P, a + b)."""
