@@ -324,10 +324,13 @@ def main():
         except Exception:
             pass
         pipes = ctx.int_pipe_peaks()
-        cbits = int(os.environ.get("OG_WINDOW_BITS", "13") or 13)
-        windows = (255 + cbits - 1) // cbits
+        def cbits(name, dflt):      # mirrors groth16.cu: pk_load (defaults 15 / 15 / 16 bits for A / B / C')
+            return int(os.environ.get(name) or os.environ.get("OG_WINDOW_BITS") or dflt)
+        win = lambda c: (255 + c - 1) // c
+        n_priv = info["n_vars"] - info["n_pub"] - 1
+        madds_per_proof_g1 = (info["n_vars"] + 2) * win(cbits("OG_C_A", 15)) + (n_priv + n_supp + m + 1) * win(cbits("OG_C_C", 16))
         # 10 field multiplications per G1 mixed add, 128 32x32->64 multiply-adds per multiplication
-        wide_mads = pairs_per_proof_g1 * windows * batch * args.steps * 10 * 128
+        wide_mads = madds_per_proof_g1 * batch * args.steps * 10 * 128
         wide_rate = wide_mads / (kms * 1e-3) if kms > 0 else 0.0
         cpu = None
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only

@@ -164,7 +164,9 @@ struct og_pk {
     og_ctx* ctx = nullptr;
     uint32_t depth = 0, n_constraints = 0, n_vars = 0, n_pub = 0, log_m = 0;
     uint32_t n_supp = 0;                 // |{i : B_query[i] != infinity}|
-    uint32_t c = 0, n_windows = 0, nb = 0;
+    // window size per MSM: index 0 = A (G1), 1 = B (G2), 2 = C' (G1); nb = 2^(c-1) buckets per proof
+    uint32_t c[3] = {0, 0, 0}, n_windows[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
+    uint32_t max_nb = 0, max_windows = 0;
     uint32_t nA = 0, nB = 0, nC = 0;     // points per MSM (incl. the folded fixed terms)
     // device
     uint32_t *a_ptr = nullptr, *a_col = nullptr, *b_ptr = nullptr, *b_col = nullptr, *supp = nullptr;
@@ -248,10 +250,16 @@ int32_t pk_load(og_ctx* ctx, const uint8_t* bytes, uint64_t len, og_pk** out) {
     for (uint32_t i = 0; i < nv; i++)
         if (!all_zero(qb1 + 64ull * i, 64) || !all_zero(qb2 + 128ull * i, 128)) supp.push_back(i);
     pk->n_supp = (uint32_t)supp.size();
-    pk->c = env_u32("OG_WINDOW_BITS", 13);
-    if (pk->c < 2 || pk->c > 16) pk->c = 13;
-    pk->n_windows = msm_windows(pk->c);
-    pk->nb = 1u << (pk->c - 1);
+    // measured on B200 (profiles/r1_window_sweep.md): 15 bits for A and B, 16 for C' (3x the points); OG_WINDOW_BITS overrides all three, OG_C_A / OG_C_B / OG_C_C one each
+    const uint32_t dflt[3] = {15, 15, 16};
+    const char* names[3] = {"OG_C_A", "OG_C_B", "OG_C_C"};
+    for (int k = 0; k < 3; k++) {
+        uint32_t c = env_u32(names[k], env_u32("OG_WINDOW_BITS", dflt[k]));
+        if (c < 2 || c > 16) c = dflt[k];
+        pk->c[k] = c; pk->n_windows[k] = msm_windows(c); pk->nb[k] = 1u << (c - 1);
+        if (pk->nb[k] > pk->max_nb) pk->max_nb = pk->nb[k];
+        if (pk->n_windows[k] > pk->max_windows) pk->max_windows = pk->n_windows[k];
+    }
     pk->nA = nv + 2; pk->nB = pk->n_supp + 2; pk->nC = n_priv + pk->n_supp + m + 1;
 
     // assemble the base-point lists in boundary bytes, then convert + extend on the GPU
@@ -269,31 +277,30 @@ int32_t pk_load(og_ctx* ctx, const uint8_t* bytes, uint64_t len, og_pk** out) {
     int32_t rc = OG_OK;
     auto fail = [&](int32_t code) { pk_free(pk); return code; };
     if ((rc = clear_flag(ctx)) != OG_OK) return fail(rc);
-    const uint32_t Wn = pk->n_windows;
     {
         uint8_t* stage;
         if ((rc = upload(ctx, &stage, hA.data(), hA.size())) != OG_OK) return fail(rc);
-        if (cudaMalloc(&pk->tabA, sizeof(G1Affine) * (size_t)pk->nA * Wn) != cudaSuccess) { cudaFree(stage); return fail(OG_E_NOMEM); }
+        if (cudaMalloc(&pk->tabA, sizeof(G1Affine) * (size_t)pk->nA * pk->n_windows[0]) != cudaSuccess) { cudaFree(stage); return fail(OG_E_NOMEM); }
         rc = g1_bytes_to_mont(ctx, stage, pk->nA, pk->tabA);
-        if (rc == OG_OK) rc = msm_build_table_g1(ctx, pk->tabA, pk->nA, pk->c, Wn);
+        if (rc == OG_OK) rc = msm_build_table_g1(ctx, pk->tabA, pk->nA, pk->c[0], pk->n_windows[0]);
         cudaStreamSynchronize(ctx->stream); cudaFree(stage);
         if (rc != OG_OK) return fail(rc);
     }
     {
         uint8_t* stage;
         if ((rc = upload(ctx, &stage, hC.data(), hC.size())) != OG_OK) return fail(rc);
-        if (cudaMalloc(&pk->tabC, sizeof(G1Affine) * (size_t)pk->nC * Wn) != cudaSuccess) { cudaFree(stage); return fail(OG_E_NOMEM); }
+        if (cudaMalloc(&pk->tabC, sizeof(G1Affine) * (size_t)pk->nC * pk->n_windows[2]) != cudaSuccess) { cudaFree(stage); return fail(OG_E_NOMEM); }
         rc = g1_bytes_to_mont(ctx, stage, pk->nC, pk->tabC);
-        if (rc == OG_OK) rc = msm_build_table_g1(ctx, pk->tabC, pk->nC, pk->c, Wn);
+        if (rc == OG_OK) rc = msm_build_table_g1(ctx, pk->tabC, pk->nC, pk->c[2], pk->n_windows[2]);
         cudaStreamSynchronize(ctx->stream); cudaFree(stage);
         if (rc != OG_OK) return fail(rc);
     }
     {
         uint8_t* stage;
         if ((rc = upload(ctx, &stage, hB.data(), hB.size())) != OG_OK) return fail(rc);
-        if (cudaMalloc(&pk->tabB, sizeof(G2Affine) * (size_t)pk->nB * Wn) != cudaSuccess) { cudaFree(stage); return fail(OG_E_NOMEM); }
+        if (cudaMalloc(&pk->tabB, sizeof(G2Affine) * (size_t)pk->nB * pk->n_windows[1]) != cudaSuccess) { cudaFree(stage); return fail(OG_E_NOMEM); }
         rc = g2_bytes_to_mont(ctx, stage, pk->nB, pk->tabB);
-        if (rc == OG_OK) rc = msm_build_table_g2(ctx, pk->tabB, pk->nB, pk->c, Wn);
+        if (rc == OG_OK) rc = msm_build_table_g2(ctx, pk->tabB, pk->nB, pk->c[1], pk->n_windows[1]);
         cudaStreamSynchronize(ctx->stream); cudaFree(stage);
         if (rc != OG_OK) return fail(rc);
     }
@@ -330,18 +337,18 @@ static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_
     b.bsc_stride = pk->nB;
     b.csc_stride = pk->nC;
     size_t max_pts = pk->nC > pk->nA ? pk->nC : pk->nA;
-    size_t n_keys = (size_t)B * pk->nb;
+    size_t n_keys = (size_t)B * pk->max_nb;
     b.W = (Fr*)ctx->slot(S_PR_WIT, sizeof(Fr) * (size_t)batch * b.w_stride);
     b.rs_m = (Fr*)ctx->slot(S_PR_MISC, sizeof(Fr) * 2 * (size_t)batch);
     b.abc = (Fr*)ctx->slot(S_PR_ABC, sizeof(Fr) * (size_t)B * 3 * m * 2);
     b.bsc = (Fr*)ctx->slot(S_PR_SCALARS, sizeof(Fr) * (size_t)B * (b.bsc_stride + b.csc_stride));
-    b.sorted = (uint32_t*)ctx->slot(S_PR_SORTED, 4 * (size_t)B * max_pts * pk->n_windows);
+    b.sorted = (uint32_t*)ctx->slot(S_PR_SORTED, 4 * (size_t)B * max_pts * pk->max_windows);
     b.counts = (uint32_t*)ctx->slot(S_PR_COUNTS, 4 * n_keys);
     b.offsets = (uint32_t*)ctx->slot(S_PR_OFFSETS, 4 * (n_keys + 1));
     b.cursor = (uint32_t*)ctx->slot(S_PR_CURSOR, 4 * n_keys);
     b.heavy = (uint32_t*)ctx->slot(S_PR_HEAVY, 4 * (n_keys + 1));
     b.bk2 = (G2XYZZ*)ctx->slot(S_PR_BUCKETS, sizeof(G2XYZZ) * n_keys);
-    b.lvl2 = (G2XYZZ*)ctx->slot(S_PR_SEG, sizeof(G2XYZZ) * msm_lvl_elems(B, pk->nb));
+    b.lvl2 = (G2XYZZ*)ctx->slot(S_PR_SEG, sizeof(G2XYZZ) * msm_lvl_elems(B, pk->max_nb));
     b.totA = (G1XYZZ*)ctx->slot(S_PR_SUMS, (sizeof(G1XYZZ) * 2 + sizeof(G2XYZZ)) * (size_t)batch);
     if (!b.W || !b.rs_m || !b.abc || !b.bsc || !b.sorted || !b.counts || !b.offsets || !b.cursor || !b.heavy || !b.bk2 || !b.lvl2 || !b.totA)
         return OG_E_NOMEM;
@@ -354,29 +361,29 @@ static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_
     return OG_OK;
 }
 
-static int32_t run_msm_g1(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t B, const G1Affine* table, uint32_t n_pts,
+static int32_t run_msm_g1(og_ctx* ctx, const og_pk* pk, int which, ChunkBufs& b, uint32_t B, const G1Affine* table, uint32_t n_pts,
                           const Fr* scalars, uint32_t stride, G1XYZZ* totals) {
     DigitPlan plan;
     plan.scalars = reinterpret_cast<const uint32_t*>(scalars);
     plan.n = n_pts; plan.scalar_stride = stride; plan.n_problems = B;
-    plan.c = pk->c; plan.n_windows = pk->n_windows; plan.nb = pk->nb;
+    plan.c = pk->c[which]; plan.n_windows = pk->n_windows[which]; plan.nb = pk->nb[which];
     plan.key_stride_problem = 1; plan.key_stride_window = 0; plan.tidx_window_stride = n_pts;
     plan.montgomery = 1;
-    uint32_t n_keys = B * pk->nb;
+    uint32_t n_keys = B * pk->nb[which];
     OG_TRY(msm_sort_digits(ctx, plan, n_keys, b.counts, b.offsets, b.cursor, b.sorted));
-    return msm_buckets_g1(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb, (uint64_t)B * n_pts * pk->n_windows, b.bk1, b.lvl1, b.heavy, b.cursor, totals);
+    return msm_buckets_g1(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb[which], (uint64_t)B * n_pts * pk->n_windows[which], b.bk1, b.lvl1, b.heavy, b.cursor, totals);
 }
-static int32_t run_msm_g2(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t B, const G2Affine* table, uint32_t n_pts,
+static int32_t run_msm_g2(og_ctx* ctx, const og_pk* pk, int which, ChunkBufs& b, uint32_t B, const G2Affine* table, uint32_t n_pts,
                           const Fr* scalars, uint32_t stride, G2XYZZ* totals) {
     DigitPlan plan;
     plan.scalars = reinterpret_cast<const uint32_t*>(scalars);
     plan.n = n_pts; plan.scalar_stride = stride; plan.n_problems = B;
-    plan.c = pk->c; plan.n_windows = pk->n_windows; plan.nb = pk->nb;
+    plan.c = pk->c[which]; plan.n_windows = pk->n_windows[which]; plan.nb = pk->nb[which];
     plan.key_stride_problem = 1; plan.key_stride_window = 0; plan.tidx_window_stride = n_pts;
     plan.montgomery = 1;
-    uint32_t n_keys = B * pk->nb;
+    uint32_t n_keys = B * pk->nb[which];
     OG_TRY(msm_sort_digits(ctx, plan, n_keys, b.counts, b.offsets, b.cursor, b.sorted));
-    return msm_buckets_g2(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb, (uint64_t)B * n_pts * pk->n_windows, b.bk2, b.lvl2, b.heavy, b.cursor, totals);
+    return msm_buckets_g2(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb[which], (uint64_t)B * n_pts * pk->n_windows[which], b.bk2, b.lvl2, b.heavy, b.cursor, totals);
 }
 
 // proofs [off, off+B): everything between the witness rows (already in b.W) and the per-proof MSM totals
@@ -392,9 +399,9 @@ static int32_t prove_chunk(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t 
     OG_LAUNCH(ctx, k_compose, dim3((mx + 127) / 128, B), 128, 0, W, b.w_stride, rs_m, pk->supp, pk->n_supp, pk->n_vars, pk->n_pub, m,
               b.bsc, b.bsc_stride, b.csc, b.csc_stride);
     OG_LAUNCH(ctx, k_pointwise, dim3((m + 127) / 128, B), 128, 0, b.abc, pk->log_m, B, b.csc, b.csc_stride, n_priv + pk->n_supp);
-    OG_TRY(run_msm_g1(ctx, pk, b, B, pk->tabA, pk->nA, W, b.w_stride, b.totA + off));
-    OG_TRY(run_msm_g1(ctx, pk, b, B, pk->tabC, pk->nC, b.csc, b.csc_stride, b.totC + off));
-    OG_TRY(run_msm_g2(ctx, pk, b, B, pk->tabB, pk->nB, b.bsc, b.bsc_stride, b.totB + off));
+    OG_TRY(run_msm_g1(ctx, pk, 0, b, B, pk->tabA, pk->nA, W, b.w_stride, b.totA + off));
+    OG_TRY(run_msm_g1(ctx, pk, 2, b, B, pk->tabC, pk->nC, b.csc, b.csc_stride, b.totC + off));
+    OG_TRY(run_msm_g2(ctx, pk, 1, b, B, pk->tabB, pk->nB, b.bsc, b.bsc_stride, b.totB + off));
     return OG_OK;
 }
 

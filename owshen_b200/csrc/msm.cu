@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restric
 // tile of one problem's scalars, histograms its digits in shared memory and touches global memory once per
 // bucket instead of once per digit (5-20x fewer global atomics); in the scatter pass it reserves a contiguous
 // run per bucket, so the 4-byte entries of a tile land in runs instead of isolated sectors.
-constexpr uint32_t DIG_TILE = 4096, DIG_THREADS = 256, DIG_MAX_NB = 4096;
+constexpr uint32_t DIG_TILE = 4096, DIG_THREADS = 256, DIG_MAX_NB = 4096, DIG_MAX_NB_COUNT = 32768;
 
 struct DigitIter {
     uint32_t s[9];
@@ -167,7 +167,7 @@ struct DigitIter {
 template <bool SCATTER>
 __global__ void __launch_bounds__(DIG_THREADS) k_digits_tiled(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                                                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
-    __shared__ uint32_t hist[DIG_MAX_NB];
+    extern __shared__ uint32_t hist[];                    // nb counters (dynamic: up to 128 KB in the count pass)
     __shared__ uint32_t base[SCATTER ? DIG_MAX_NB : 1];
     const uint32_t prob = blockIdx.y, nb = P.nb;
     const uint64_t lo = (uint64_t)blockIdx.x * DIG_TILE;
@@ -266,10 +266,15 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
         OG_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * ((size_t)n_keys + 1), ctx->stream));
         return OG_OK;
     }
-    const bool tiled = plan.key_stride_window == 0 && plan.nb <= DIG_MAX_NB;
+    const bool tiled = plan.key_stride_window == 0 && plan.nb <= DIG_MAX_NB_COUNT;
+    static bool smem_opt_in = false;
+    if (tiled && !smem_opt_in) {
+        OG_CUDA(ctx, cudaFuncSetAttribute(k_digits_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * DIG_MAX_NB_COUNT)));
+        smem_opt_in = true;
+    }
     dim3 grid((unsigned)((plan.n + 255) / 256), plan.n_problems);
     dim3 tgrid((unsigned)((plan.n + DIG_TILE - 1) / DIG_TILE), plan.n_problems);
-    if (tiled) OG_LAUNCHN(ctx, "k_digits_tiled<count>", k_digits_tiled<false>, tgrid, DIG_THREADS, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
+    if (tiled) OG_LAUNCHN(ctx, "k_digits_tiled<count>", k_digits_tiled<false>, tgrid, DIG_THREADS, 4 * (size_t)plan.nb, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
     else OG_LAUNCH(ctx, k_digits<false>, grid, 256, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
     {   // offsets[n_keys] receives the grand total; the tile sums live in the cursor array (zeroed again below)
         uint32_t n_tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
@@ -281,7 +286,7 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
     // measured: the tiled scatter (run reservation + shared-memory ranks) is slower than the plain one
     // (39 vs 33 ms per 1024 proofs) while the tiled count is 5x faster (5 vs 24 ms) -> tiled count, plain scatter
     static const int tiled_scatter = [] { const char* v = getenv("OG_TILED_SCATTER"); return v ? atoi(v) : 0; }();
-    if (tiled && tiled_scatter) OG_LAUNCHN(ctx, "k_digits_tiled<scatter>", k_digits_tiled<true>, tgrid, DIG_THREADS, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
+    if (tiled && tiled_scatter && plan.nb <= DIG_MAX_NB) OG_LAUNCHN(ctx, "k_digits_tiled<scatter>", k_digits_tiled<true>, tgrid, DIG_THREADS, 4 * (size_t)plan.nb, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
     else OG_LAUNCH(ctx, k_digits<true>, grid, 256, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
     return OG_OK;
 }
@@ -398,16 +403,18 @@ __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__
     const XYZZ<F>* S = S_in + (size_t)g * n_in;
     const XYZZ<F>* U = U_in ? U_in + (size_t)g * n_in : nullptr;
     uint32_t lo = p * RED_FAN, hi = min(n_in, lo + RED_FAN);
+    // group operations inlined here: with 2^15 buckets per proof this kernel is 10 % of a proving step, and the
+    // out-of-line versions move every operand through local memory
     XYZZ<F> R = XYZZ<F>::inf(), T = XYZZ<F>::inf(), Us = XYZZ<F>::inf();
     for (uint32_t i = hi - 1; i > lo; i--) {
-        xyzz_add_ni(&R, &S[i]);
-        xyzz_add_ni(&T, &R);
-        if (U) xyzz_add_ni(&Us, &U[i]);
+        R.add(S[i]);
+        T.add(R);
+        if (U) Us.add(U[i]);
     }
-    xyzz_add_ni(&R, &S[lo]);
-    if (U) xyzz_add_ni(&Us, &U[lo]);
-    for (uint32_t k = 0; k < w_log2; k++) xyzz_dbl_ni(&T);
-    xyzz_add_ni(&Us, &T);
+    R.add(S[lo]);
+    if (U) Us.add(U[lo]);
+    for (uint32_t k = 0; k < w_log2; k++) T = T.dbl();
+    Us.add(T);
     S_out[(size_t)g * n_out + p] = R;
     U_out[(size_t)g * n_out + p] = Us;
 }
