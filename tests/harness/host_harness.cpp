@@ -65,3 +65,13 @@ extern "C" void ht_bjj_verify(const uint8_t* pk_x, const uint8_t* pk_odd, const 
                                 [](const Fr* in) { return in[0] * in[1] * in[2] * in[3] * in[4]; });
     }
 }
+
+// ---- wide products / separate reduction (fp.cuh: mul_wide, sqr_wide, mont_reduce_wide) ----------------------
+extern "C" void ht_wide(const uint8_t* a, const uint8_t* b, uint8_t* mul32, uint8_t* sqr32, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) {
+        Fq x = load<Fq>(a + 32 * i), y = load<Fq>(b + 32 * i), r;
+        uint32_t T[16];
+        mul_wide(T, x.l, y.l); mont_reduce_wide<FqParams>(r.l, T); store(mul32 + 32 * i, r);
+        sqr_wide(T, x.l); mont_reduce_wide<FqParams>(r.l, T); store(sqr32 + 32 * i, r);
+    }
+}

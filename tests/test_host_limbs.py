@@ -92,3 +92,26 @@ def test_babyjubjub_verification_core_on_host(h):
     out = C.create_string_buffer(len(odd))
     h.ht_bjj_verify(pkx, odd, m, s, len(odd), bn.fr_to_bytes(bjj.BASE[0]) + bn.fr_to_bytes(bjj.BASE[1]), out)
     assert list(out.raw) == [1 if e else 0 for e in expect] + [2]
+
+
+def test_wide_products_and_separate_reduction(h):
+    """mul_wide / sqr_wide / mont_reduce_wide (squarings and the lazy Fq2 product are built on them)."""
+    rng = random.Random(6)
+    xs = [rng.randrange(P) for _ in range(3000)] + [0, 1, P - 1, P - 1, 2**253, P - 2, 2**32 - 1]
+    ys = [rng.randrange(P) for _ in range(3000)] + [P - 1, P - 1, P - 1, 1, 2**253, P - 2, 2**224]
+    n = len(xs)
+    m = C.create_string_buffer(32 * n); s = C.create_string_buffer(32 * n)
+    h.ht_wide(cport.fqs(xs), cport.fqs(ys), m, s, C.c_uint64(n))
+    assert cport.unfr(m.raw) == [a * b % P for a, b in zip(xs, ys)]
+    assert cport.unfr(s.raw) == [a * a % P for a in xs]
+
+
+def test_lazy_fq2_product_extremes(h):
+    rng = random.Random(7)
+    cases = [((rng.randrange(P), rng.randrange(P)), (rng.randrange(P), rng.randrange(P))) for _ in range(500)]
+    cases += [((0, P - 1), (0, P - 1)), ((P - 1, 0), (P - 1, 0)), ((P - 1, P - 1), (P - 1, P - 1)), ((P - 1, 1), (P - 1, 1)),
+              ((1, P - 1), (1, P - 1)), ((P - 2, P - 1), (P - 1, P - 2)), ((0, 0), (5, 7)), ((0, P - 1), (P - 1, 0))]
+    o = C.create_string_buffer(64)
+    for a, b in cases:
+        h.ht_fq2_mul(cport.fqs(a), cport.fqs(b), o)
+        assert tuple(cport.unfr(o.raw)) == bn.f2_mul(a, b), (a, b)
