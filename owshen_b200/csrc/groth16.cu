@@ -2,8 +2,8 @@
 // development setup.  The reference has no prover; conventions are frozen in
 // DESIGN.md section 4 and checked bit-for-bit against oracle/groth16.py and oracle/cpu.
 //
-// Per chunk of B proofs (everything stays in HBM, nothing returns to the host until the proofs):
-//   witness      k_withdraw_witness (mimc.cu): MiMC7 Merkle path + every round value  -> W[B][n_vars+2]
+// Once per batch:  witness  k_withdraw_witness (mimc.cu): MiMC7 Merkle path + every round value -> W[batch][n_vars+2]
+// Per chunk of B proofs (default 256; everything stays in HBM, nothing returns to the host until the proofs):
 //   a, b, c      k_abc: sparse A.w, B.w over the CSR kept in L2, c = a*b
 //   h            3 iNTT + 3 coset NTT (ntt.cu), k_pointwise: d = a'b' - c' written straight into
 //                the scalar vector of the C multi-scalar multiplication
@@ -12,7 +12,7 @@
 //                  A  = <[A_query; alpha1; delta1],           [w; 1; r]>                 (G1)
 //                  B  = <[B2_query|supp; beta2; delta2],      [w|supp; 1; s]>            (G2)
 //                  C' = <[L_query; B1_query|supp; H_query; beta1], [w_priv; r*w|supp; d; r]>  (G1)
-//   assemble     C = C' + s*A  (the only variable-base scalar multiplication), affine, bytes.
+// Once per batch:  assemble  C = C' + s*A  (the only variable-base scalar multiplication), affine, bytes.
 // Identity used: s*A + r*B1 - r*s*delta1 = s*A + r*beta1 + sum (r*w_i) B1_i.
 #include "groth16.cuh"
 #include "mimc.cuh"

@@ -84,52 +84,8 @@ int32_t g2_mont_to_bytes(og_ctx* ctx, const G2Affine* d_in, uint64_t n, uint8_t*
 
 #ifdef OG_MSM_G1
 // ---- 1/3: digits -> histogram / scatter ---------------------------------------------------------------
-template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                                                uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t prob = blockIdx.y;
-    if (i >= P.n) return;
-    const uint32_t* sp = P.scalars + ((uint64_t)prob * P.scalar_stride + i) * 8;
-    uint32_t s[9];
-    if (P.montgomery) {
-        Fr v;
-#pragma unroll
-        for (int j = 0; j < 8; j++) v.l[j] = sp[j];
-        v.to_canonical(s);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; j++) s[j] = sp[j];
-        if (!Fr::canonical_lt_mod(s)) { atomicOr(flag, 1); return; }
-    }
-    s[8] = 0;
-    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) return;
-    const uint32_t c = P.c, half = 1u << (c - 1), mask = (1u << c) - 1;
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < P.n_windows; w++) {
-        uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
-        uint64_t two = ((uint64_t)s[word + 1] << 32) | s[word];     // word <= 7 because n_windows*c <= 255 + c
-        uint32_t v = ((uint32_t)(two >> sh) & mask) + carry;
-        uint32_t neg = v > half;
-        uint32_t mag = neg ? (1u << c) - v : v;
-        carry = neg;
-        if (mag == 0) continue;
-        uint32_t key = (prob * P.key_stride_problem + w * P.key_stride_window) * P.nb + (mag - 1);
-        if (!SCATTER) {
-            atomicAdd(&counts[key], 1u);
-        } else {
-            uint32_t pos = offsets[key] + atomicAdd(&cursor[key], 1u);
-            sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
-        }
-    }
-}
-
-// Tiled variant for groups with nb <= 4096 buckets (the batched prover: one group per proof).  A CTA owns a
-// tile of one problem's scalars, histograms its digits in shared memory and touches global memory once per
-// bucket instead of once per digit (5-20x fewer global atomics); in the scatter pass it reserves a contiguous
-// run per bucket, so the 4-byte entries of a tile land in runs instead of isolated sectors.
-constexpr uint32_t DIG_TILE = 4096, DIG_THREADS = 256, DIG_MAX_NB = 4096, DIG_MAX_NB_COUNT = 32768;
-
+// Signed c-bit digits of one scalar: v = bits + carry; v > 2^(c-1) -> digit v - 2^c, carry 1.  n_windows*c >= 255
+// guarantees that the top window absorbs the last carry for every scalar < r < 2^254.
 struct DigitIter {
     uint32_t s[9];
     __device__ __forceinline__ bool load(const DigitPlan& P, uint32_t prob, uint64_t i, int* flag) {
@@ -164,6 +120,32 @@ struct DigitIter {
     }
 };
 
+// one thread per scalar, global atomics (one-shot MSMs: up to 2^15 buckets x 16 windows of keys)
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
+                                                uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t prob = blockIdx.y;
+    if (i >= P.n) return;
+    DigitIter it;
+    if (!it.load(P, prob, i, flag)) return;
+    it.for_each(P, [&](uint32_t w, uint32_t b, uint32_t neg) {
+        uint32_t key = (prob * P.key_stride_problem + w * P.key_stride_window) * P.nb + b;
+        if (!SCATTER) {
+            atomicAdd(&counts[key], 1u);
+        } else {
+            uint32_t pos = offsets[key] + atomicAdd(&cursor[key], 1u);
+            sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
+        }
+    });
+}
+
+// Tiled variant for groups with nb <= 4096 buckets (the batched prover: one group per proof).  A CTA owns a
+// tile of one problem's scalars, histograms its digits in shared memory and touches global memory once per
+// bucket instead of once per digit (5-20x fewer global atomics); in the scatter pass it reserves a contiguous
+// run per bucket, so the 4-byte entries of a tile land in runs instead of isolated sectors.
+constexpr uint32_t DIG_TILE = 4096, DIG_THREADS = 256, DIG_MAX_NB = 4096, DIG_MAX_NB_COUNT = 32768;
+
 template <bool SCATTER>
 __global__ void __launch_bounds__(DIG_THREADS) k_digits_tiled(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                                                               uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
@@ -180,10 +162,9 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits_tiled(DigitPlan P, uint3
         if (it.load(P, prob, i, flag)) it.for_each(P, [&](uint32_t, uint32_t b, uint32_t) { atomicAdd(&hist[b], 1u); });
     }
     __syncthreads();
-    if (!SCATTER) {
+    if constexpr (!SCATTER) {
         for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) if (hist[b]) atomicAdd(&counts[key0 + b], hist[b]);
-        return;
-    }
+    } else {
     for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) {
         uint32_t h = hist[b];
         base[b] = h ? offsets[key0 + b] + atomicAdd(&cursor[key0 + b], h) : 0;
@@ -197,6 +178,7 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits_tiled(DigitPlan P, uint3
                 uint32_t pos = base[b] + atomicAdd(&hist[b], 1u);
                 sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
             });
+    }
     }
 }
 
