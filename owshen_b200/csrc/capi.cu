@@ -52,6 +52,14 @@ int32_t check_flag(og_ctx* ctx) {
 }
 }  // namespace og
 
+// every entry point that takes a ctx first makes its device current: several contexts (one per GPU) may live in
+// one process (one Prover per GPU), and launches go to the calling thread's current device
+#define OG_ENTER(ctx)                                                                              \
+    do {                                                                                           \
+        if (!(ctx)) return OG_E_INVALID;                                                           \
+        OG_CUDA(ctx, cudaSetDevice((ctx)->device));                                                \
+    } while (0)
+
 #define H2D(ctx, dst, src, bytes) OG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (ctx)->stream))
 #define D2H(ctx, dst, src, bytes) OG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (ctx)->stream))
 
@@ -114,16 +122,19 @@ void og_free(og_ctx* ctx) {
 }
 
 int32_t og_sync(og_ctx* ctx) {
+    OG_ENTER(ctx);
     if (!ctx) return OG_E_INVALID;
     OG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return OG_OK;
 }
 int32_t og_timer_start(og_ctx* ctx) {
+    OG_ENTER(ctx);
     if (!ctx) return OG_E_INVALID;
     OG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     return OG_OK;
 }
 int32_t og_timer_stop(og_ctx* ctx, float* ms) {
+    OG_ENTER(ctx);
     if (!ctx || !ms) return OG_E_INVALID;
     OG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     OG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
@@ -133,12 +144,14 @@ int32_t og_timer_stop(og_ctx* ctx, float* ms) {
 uint64_t og_launch_count(const og_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int32_t og_profile(og_ctx* ctx, int32_t enable) {
+    OG_ENTER(ctx);
     if (!ctx) return OG_E_INVALID;
     ctx->prof_on = enable != 0;
     return OG_OK;
 }
 // "name,launches,total_ms\n" per kernel since the last dump; synchronises the stream
 int32_t og_profile_dump(og_ctx* ctx, char* buf, uint64_t cap) {
+    OG_ENTER(ctx);
     if (!ctx || !buf || cap == 0) return OG_E_INVALID;
     OG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     struct Agg { const char* name; uint64_t n; double ms; };
@@ -278,6 +291,7 @@ __global__ void __launch_bounds__(256) k_dfma(double* out, uint32_t iters, doubl
 extern "C" {
 
 int32_t og_mul_latency(og_ctx* ctx, double* cycles_dependent, double* cycles_two_chains) {
+    OG_ENTER(ctx);
     if (!ctx || !cycles_dependent || !cycles_two_chains) return OG_E_INVALID;
     OG_SLOT(ctx, io, Fr, S_IO_A, sizeof(Fr) * 96 + 64);
     long long* d_cyc = reinterpret_cast<long long*>(io + 96);
@@ -296,6 +310,7 @@ int32_t og_mul_latency(og_ctx* ctx, double* cycles_dependent, double* cycles_two
 }
 
 int32_t og_fp64_peak(og_ctx* ctx, double* dfma_per_s) {
+    OG_ENTER(ctx);
     if (!ctx || !dfma_per_s) return OG_E_INVALID;
     OG_SLOT(ctx, d_out, double, S_IO_A, 64);
     const uint32_t iters = 2048, ctas = ctx->sm_count * 8, threads = 256;
@@ -315,12 +330,14 @@ int32_t og_fp64_peak(og_ctx* ctx, double* dfma_per_s) {
 }
 
 int32_t og_imad_peak(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s) {
+    OG_ENTER(ctx);
     if (!ctx || !mad_per_s || !wide_mad_per_s) return OG_E_INVALID;
     double chain = 0;
     return og_int_pipe_peaks(ctx, mad_per_s, wide_mad_per_s, &chain);
 }
 
 int32_t og_int_pipe_peaks(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s, double* carry_chain_wide_per_s) {
+    OG_ENTER(ctx);
     if (!ctx || !mad_per_s || !wide_mad_per_s || !carry_chain_wide_per_s) return OG_E_INVALID;
     OG_SLOT(ctx, d_out, uint32_t, S_IO_A, 64);
     const uint32_t iters = 2048, ctas = ctx->sm_count * 8, threads = 256;
@@ -346,6 +363,7 @@ int32_t og_int_pipe_peaks(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s
 }
 
 int32_t og_field_op(og_ctx* ctx, int32_t field, int32_t op, const uint8_t* a, const uint8_t* b, uint64_t n, uint8_t* out) {
+    OG_ENTER(ctx);
     if (!ctx || !a || !b || !out || field < 0 || field > 1 || op < 0 || op > 2) return OG_E_INVALID;
     if (n == 0) return OG_OK;
     OG_SLOT(ctx, da, uint8_t, S_IO_A, 32 * n);
@@ -371,6 +389,7 @@ int32_t og_mimc7_constants(uint8_t* out, uint32_t* n_rounds) {
 }
 
 int32_t og_mimc7_hash2(og_ctx* ctx, const uint8_t* left, const uint8_t* right, uint64_t n, uint8_t* out) {
+    OG_ENTER(ctx);
     if (!ctx || !left || !right || !out) return OG_E_INVALID;
     if (n == 0) return OG_OK;
     OG_SLOT(ctx, da, uint8_t, S_IO_A, 32 * n);
@@ -385,12 +404,14 @@ int32_t og_mimc7_hash2(og_ctx* ctx, const uint8_t* left, const uint8_t* right, u
 
 int32_t og_mimc7_merkle_paths_dev(og_ctx* ctx, const uint8_t* d_leaves, const uint8_t* d_siblings, const uint32_t* d_path_bits,
                                   uint32_t n_paths, uint32_t depth, uint8_t* d_out_nodes) {
+    OG_ENTER(ctx);
     if (!ctx || !d_leaves || !d_siblings || !d_path_bits || !d_out_nodes || depth > 32) return OG_E_INVALID;
     return mimc_merkle_paths_dev(ctx, d_leaves, d_siblings, d_path_bits, n_paths, depth, d_out_nodes);
 }
 
 int32_t og_mimc7_merkle_paths(og_ctx* ctx, const uint8_t* leaves, const uint8_t* siblings, const uint32_t* path_bits,
                               uint32_t n_paths, uint32_t depth, uint8_t* out_nodes) {
+    OG_ENTER(ctx);
     if (!ctx || !leaves || !siblings || !path_bits || !out_nodes || depth > 32) return OG_E_INVALID;
     if (n_paths == 0) return OG_OK;
     size_t nl = 32ull * n_paths, ns = 32ull * n_paths * depth, no = 32ull * n_paths * (depth + 1);
@@ -408,6 +429,7 @@ int32_t og_mimc7_merkle_paths(og_ctx* ctx, const uint8_t* leaves, const uint8_t*
 }
 
 int32_t og_mimc7_merkle_build(og_ctx* ctx, const uint8_t* leaves, uint64_t n, uint8_t* out_levels) {
+    OG_ENTER(ctx);
     if (!ctx || !leaves || !out_levels || n == 0 || (n & (n - 1)) || n > (1ull << 28)) return OG_E_INVALID;
     uint64_t total = 2 * n - 1;
     OG_SLOT(ctx, din, uint8_t, S_IO_A, 32 * n);
@@ -425,6 +447,7 @@ int32_t og_mimc7_merkle_build(og_ctx* ctx, const uint8_t* leaves, uint64_t n, ui
 // ---- BabyJubJub (the reference's own signature scheme, babyjubjub/mod.rs) -----------------------------------
 int32_t og_bjj_verify_batch(og_ctx* ctx, const uint8_t* pk_x, const uint8_t* pk_is_odd, const uint8_t* messages, const uint8_t* signatures,
                             uint32_t n, int32_t hash_kind, uint8_t* out_status) {
+    OG_ENTER(ctx);
     if (!ctx || !pk_x || !pk_is_odd || !messages || !signatures || !out_status || hash_kind < 0 || hash_kind > 1) return OG_E_INVALID;
     if (n == 0) return OG_OK;
     OG_SLOT(ctx, dx, uint8_t, S_IO_A, 32ull * n);
@@ -441,14 +464,17 @@ int32_t og_bjj_verify_batch(og_ctx* ctx, const uint8_t* pk_x, const uint8_t* pk_
 
 // ---- MSM --------------------------------------------------------------------------------------------------
 int32_t og_msm_g1_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out64) {
+    OG_ENTER(ctx);
     if (!ctx || !d_out64 || (n && (!d_points || !d_scalars))) return OG_E_INVALID;
     return msm_g1_dev(ctx, d_points, d_scalars, n, d_out64);
 }
 int32_t og_msm_g2_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out128) {
+    OG_ENTER(ctx);
     if (!ctx || !d_out128 || (n && (!d_points || !d_scalars))) return OG_E_INVALID;
     return msm_g2_dev(ctx, d_points, d_scalars, n, d_out128);
 }
 int32_t og_msm_g1(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out64) {
+    OG_ENTER(ctx);
     if (!ctx || !out64 || (n && (!points || !scalars))) return OG_E_INVALID;
     OG_SLOT(ctx, dp, uint8_t, S_IO_A, 64 * n);
     OG_SLOT(ctx, ds, uint8_t, S_IO_B, 32 * n);
@@ -460,6 +486,7 @@ int32_t og_msm_g1(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, ui
     return check_flag(ctx);
 }
 int32_t og_msm_g2(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out128) {
+    OG_ENTER(ctx);
     if (!ctx || !out128 || (n && (!points || !scalars))) return OG_E_INVALID;
     OG_SLOT(ctx, dp, uint8_t, S_IO_A, 128 * n);
     OG_SLOT(ctx, ds, uint8_t, S_IO_B, 32 * n);
@@ -471,6 +498,7 @@ int32_t og_msm_g2(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, ui
     return check_flag(ctx);
 }
 int32_t og_g1_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out64) {
+    OG_ENTER(ctx);
     if (!ctx || !out64 || (n && !points)) return OG_E_INVALID;
     OG_SLOT(ctx, dp, uint8_t, S_IO_A, 64 * n);
     OG_SLOT(ctx, dout, uint8_t, S_IO_C, 64);
@@ -481,6 +509,7 @@ int32_t og_g1_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out64
     return check_flag(ctx);
 }
 int32_t og_g2_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out128) {
+    OG_ENTER(ctx);
     if (!ctx || !out128 || (n && !points)) return OG_E_INVALID;
     OG_SLOT(ctx, dp, uint8_t, S_IO_A, 128 * n);
     OG_SLOT(ctx, dout, uint8_t, S_IO_C, 128);
@@ -493,6 +522,7 @@ int32_t og_g2_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out12
 
 // out[i] = scalars[i] * G (fixed-base, generator of G1 / G2): used by the setup and to synthesise MSM inputs
 int32_t og_g1_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uint8_t* out_points) {
+    OG_ENTER(ctx);
     if (!ctx || (n && (!scalars || !out_points))) return OG_E_INVALID;
     if (n == 0) return OG_OK;
     OG_SLOT(ctx, ds, uint8_t, S_IO_A, 32 * n);
@@ -506,6 +536,7 @@ int32_t og_g1_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uin
     return check_flag(ctx);
 }
 int32_t og_g2_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uint8_t* out_points) {
+    OG_ENTER(ctx);
     if (!ctx || (n && (!scalars || !out_points))) return OG_E_INVALID;
     if (n == 0) return OG_OK;
     OG_SLOT(ctx, ds, uint8_t, S_IO_A, 32 * n);
@@ -521,6 +552,7 @@ int32_t og_g2_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uin
 
 // ---- NTT ----------------------------------------------------------------------------------------------------
 int32_t og_ntt_dev(og_ctx* ctx, uint8_t* d_data, uint32_t log_n, uint32_t batch, int32_t inverse, int32_t coset) {
+    OG_ENTER(ctx);
     if (!ctx || !d_data || log_n > 27 || !aligned32(d_data)) return OG_E_INVALID;
     uint64_t tot = (uint64_t)batch << log_n;
     if (tot == 0) return OG_OK;
@@ -530,6 +562,7 @@ int32_t og_ntt_dev(og_ctx* ctx, uint8_t* d_data, uint32_t log_n, uint32_t batch,
     return mimc_from_mont_dev(ctx, work, tot, d_data);
 }
 int32_t og_ntt(og_ctx* ctx, uint8_t* data, uint32_t log_n, uint32_t batch, int32_t inverse, int32_t coset) {
+    OG_ENTER(ctx);
     if (!ctx || !data || log_n > 27) return OG_E_INVALID;
     uint64_t tot = (uint64_t)batch << log_n;
     if (tot == 0) return OG_OK;
@@ -564,6 +597,7 @@ int32_t og_withdraw_r1cs_export(uint32_t depth, int32_t which, uint32_t* row_ptr
 }
 int32_t og_withdraw_witness(og_ctx* ctx, uint32_t depth, const uint8_t* nullifiers, const uint8_t* secrets, const uint8_t* recipients,
                             const uint8_t* siblings, const uint32_t* path_bits, uint32_t batch, uint8_t* witnesses) {
+    OG_ENTER(ctx);
     if (!ctx || depth == 0 || depth > 32 || !nullifiers || !secrets || !recipients || !siblings || !path_bits || !witnesses) return OG_E_INVALID;
     if (batch == 0) return OG_OK;
     WithdrawLayout L = WithdrawLayout::make(depth);
@@ -584,10 +618,12 @@ int32_t og_withdraw_witness(og_ctx* ctx, uint32_t depth, const uint8_t* nullifie
 // ---- Groth16 -------------------------------------------------------------------------------------------------------
 int32_t og_groth16_setup_withdraw(og_ctx* ctx, uint32_t depth, const uint8_t* toxic160, uint8_t* pk_out, uint64_t* pk_len,
                                   uint8_t* vk_out, uint64_t* vk_len) {
+    OG_ENTER(ctx);
     if (!ctx || !pk_len || !vk_len || ((pk_out || vk_out) && !toxic160)) return OG_E_INVALID;
     return setup_withdraw(ctx, depth, toxic160, pk_out, pk_len, vk_out, vk_len);
 }
 int32_t og_load_pk(og_ctx* ctx, const uint8_t* pk_bytes, uint64_t len, og_pk** out) {
+    OG_ENTER(ctx);
     if (!ctx || !pk_bytes || !out) return OG_E_INVALID;
     return pk_load(ctx, pk_bytes, len, out);
 }
@@ -599,6 +635,7 @@ int32_t og_pk_info(const og_pk* pk, uint32_t* n_vars, uint32_t* n_pub, uint32_t*
 }
 
 int32_t og_groth16_prove(og_ctx* ctx, const og_pk* pk, const uint8_t* witnesses, uint32_t batch, const uint8_t* rs, uint8_t* proofs) {
+    OG_ENTER(ctx);
     if (!ctx || !pk || !witnesses || !rs || !proofs) return OG_E_INVALID;
     if (batch == 0) return OG_OK;
     uint32_t nv; pk_info(pk, &nv, nullptr, nullptr, nullptr);
@@ -615,6 +652,7 @@ int32_t og_groth16_prove(og_ctx* ctx, const og_pk* pk, const uint8_t* witnesses,
 int32_t og_groth16_prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_nullifiers, const uint8_t* d_secrets,
                                       const uint8_t* d_recipients, const uint8_t* d_siblings, const uint32_t* d_path_bits, uint32_t batch,
                                       const uint8_t* d_rs, uint8_t* d_proofs, uint8_t* d_public_out) {
+    OG_ENTER(ctx);
     if (!ctx || !pk || !d_nullifiers || !d_secrets || !d_recipients || !d_siblings || !d_path_bits || !d_rs || !d_proofs) return OG_E_INVALID;
     return prove_withdraw_dev(ctx, pk, d_nullifiers, d_secrets, d_recipients, d_siblings, d_path_bits, batch, d_rs, d_proofs, d_public_out);
 }
@@ -622,6 +660,7 @@ int32_t og_groth16_prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_
 int32_t og_groth16_prove_withdraw(og_ctx* ctx, const og_pk* pk, const uint8_t* nullifiers, const uint8_t* secrets, const uint8_t* recipients,
                                   const uint8_t* siblings, const uint32_t* path_bits, uint32_t batch, const uint8_t* rs, uint8_t* proofs,
                                   uint8_t* public_out) {
+    OG_ENTER(ctx);
     if (!ctx || !pk || !nullifiers || !secrets || !recipients || !siblings || !path_bits || !rs || !proofs) return OG_E_INVALID;
     if (batch == 0) return OG_OK;
     uint32_t depth, n_pub; pk_info(pk, nullptr, &n_pub, nullptr, &depth);
@@ -644,6 +683,7 @@ int32_t og_groth16_prove_withdraw(og_ctx* ctx, const og_pk* pk, const uint8_t* n
 }
 
 int32_t og_groth16_h_evals(og_ctx* ctx, const og_pk* pk, const uint8_t* witness, uint8_t* out) {
+    OG_ENTER(ctx);
     if (!ctx || !pk || !witness || !out) return OG_E_INVALID;
     uint32_t nv, log_m; pk_info(pk, &nv, nullptr, &log_m, nullptr);
     OG_SLOT(ctx, dw, uint8_t, S_IO_A, 32ull * nv);

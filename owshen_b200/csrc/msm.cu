@@ -249,10 +249,9 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
         return OG_OK;
     }
     const bool tiled = plan.key_stride_window == 0 && plan.nb <= DIG_MAX_NB_COUNT;
-    static bool smem_opt_in = false;
-    if (tiled && !smem_opt_in) {
+    if (tiled && !ctx->digits_smem_opt_in) {      // per device, hence per context
         OG_CUDA(ctx, cudaFuncSetAttribute(k_digits_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * DIG_MAX_NB_COUNT)));
-        smem_opt_in = true;
+        ctx->digits_smem_opt_in = true;
     }
     dim3 grid((unsigned)((plan.n + 255) / 256), plan.n_problems);
     dim3 tgrid((unsigned)((plan.n + DIG_TILE - 1) / DIG_TILE), plan.n_problems);

@@ -293,3 +293,24 @@ def test_pk_blob_rejects_garbage(ctx, keys32):
         ob.ProvingKey(ctx, b"NOPE" + pk[4:])
     with pytest.raises(ob.OwshenB200Error):
         ob.ProvingKey(ctx, pk[:len(pk) // 2])
+
+
+def test_two_contexts_in_one_process(ctx):
+    """One context per GPU inside one process (one Prover per GPU): interleaved calls must each
+    run on their own device.  Needs two GPUs; skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = random.Random(31)
+    c1 = ob.Context(1)
+    try:
+        pts = rand_g1(rng, 500)
+        sc = cport.frs([rng.randrange(R) for _ in range(500)])
+        exp = cport.g1_msm(pts, sc)
+        for _ in range(3):
+            assert ctx.msm_g1(pts, sc) == exp
+            assert c1.msm_g1(pts, sc) == exp
+        x, y = cport.frs([3, 5]), cport.frs([7, 11])
+        assert c1.mimc7_hash2(x, y) == ctx.mimc7_hash2(x, y)
+    finally:
+        c1.close()
