@@ -380,36 +380,56 @@ def verify(vk_bytes: bytes, public_inputs: bytes, proof: bytes) -> bool:
 
 
 class MerkleTree:
-    """Fixed-depth sparse MiMC7 Merkle tree; every hash runs in the CUDA library.
+    """Fixed-depth sparse MiMC7 Merkle tree; every hash runs in the CUDA library, nodes live behind a
+    KvStore-shaped interface (owshen_b200/kvstore.py, mirroring /root/reference/src/db/mod.rs:24-52), so a tree
+    can be reopened over the same store.
 
-    insert_batch() appends leaves and rehashes only the touched ancestors, one batched
-    og_mimc7_hash2 launch per level.  path(i) returns (siblings bytes, path_bits int)."""
+    insert_batch() appends leaves and rehashes only the touched ancestors, one batched og_mimc7_hash2 launch
+    per level, one batch_put per call.  path(i) returns (siblings bytes, path_bits int)."""
 
-    def __init__(self, ctx: Context, depth: int):
+    def __init__(self, ctx: Context, depth: int, store=None, prefix: bytes = b"mt/"):
+        from .kvstore import RamKvStore
         assert 1 <= depth <= 32
         self.ctx, self.depth = ctx, depth
+        self.store = store if store is not None else RamKvStore()
+        self.prefix = prefix
         self.zeros = [bytes(32)]
         for _ in range(depth):
             self.zeros.append(ctx.mimc7_hash2(self.zeros[-1], self.zeros[-1]))
-        self.levels = [dict() for _ in range(depth + 1)]
-        self.n_leaves = 0
+        n = self.store.get_raw(prefix + b"n")
+        self.n_leaves = int.from_bytes(n, "little") if n else 0
+        d = self.store.get_raw(prefix + b"depth")
+        if d is not None and int.from_bytes(d, "little") != depth:
+            raise ValueError("store holds a tree of a different depth")
 
-    def _get(self, lvl, idx):
-        return self.levels[lvl].get(idx, self.zeros[lvl])
+    def _key(self, lvl: int, idx: int) -> bytes:
+        return self.prefix + lvl.to_bytes(1, "little") + idx.to_bytes(8, "little")
+
+    def _get(self, lvl, idx, pending=None):
+        if pending is not None:
+            v = pending.get((lvl, idx))
+            if v is not None:
+                return v
+        v = self.store.get_raw(self._key(lvl, idx))
+        return v if v is not None else self.zeros[lvl]
 
     def insert_batch(self, leaves):
         start = self.n_leaves
+        pending = {}
         for k, leaf in enumerate(leaves):
-            self.levels[0][start + k] = leaf if isinstance(leaf, (bytes, bytearray)) else fr_bytes(leaf)
-        self.n_leaves += len(leaves)
+            pending[(0, start + k)] = bytes(leaf) if isinstance(leaf, (bytes, bytearray)) else fr_bytes(leaf)
         dirty = sorted({(start + k) >> 1 for k in range(len(leaves))})
         for lvl in range(self.depth):
-            left = b"".join(self._get(lvl, 2 * p) for p in dirty)
-            right = b"".join(self._get(lvl, 2 * p + 1) for p in dirty)
+            left = b"".join(self._get(lvl, 2 * p, pending) for p in dirty)
+            right = b"".join(self._get(lvl, 2 * p + 1, pending) for p in dirty)
             out = self.ctx.mimc7_hash2(left, right)
             for k, p in enumerate(dirty):
-                self.levels[lvl + 1][p] = out[32 * k:32 * k + 32]
+                pending[(lvl + 1, p)] = out[32 * k:32 * k + 32]
             dirty = sorted({p >> 1 for p in dirty})
+        self.n_leaves += len(leaves)
+        batch = [(self._key(l, i), v) for (l, i), v in pending.items()]
+        batch += [(self.prefix + b"n", self.n_leaves.to_bytes(8, "little")), (self.prefix + b"depth", self.depth.to_bytes(1, "little"))]
+        self.store.batch_put_raw(batch)
         return list(range(start, start + len(leaves)))
 
     def insert(self, leaf) -> int:

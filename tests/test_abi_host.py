@@ -86,3 +86,12 @@ def test_host_verifier_accepts_oracle_proof_and_rejects_tampering():
     # a point that is on the curve but the proof is garbage -> False, not an exception
     g1, g2 = bn.g1_to_bytes(bn.G1_GEN), bn.g2_to_bytes(bn.G2_GEN)
     assert not ob.verify(vk, pub, g1 + g2 + g1)
+
+
+def test_kvstore_shape_matches_reference_trait():
+    # /root/reference/src/db/mod.rs:24-52: get_raw, batch_put_raw, None deletes
+    s = ob.RamKvStore()
+    s.batch_put_raw([(b"k1", b"v1"), (b"k2", b"v2")])
+    assert s.get_raw(b"k1") == b"v1" and s.get_raw(b"missing") is None
+    s.batch_put_raw([(b"k1", None)])
+    assert s.get_raw(b"k1") is None and s.get_raw(b"k2") == b"v2"

@@ -94,6 +94,14 @@ def test_merkle_tree_api(ctx):
     sibs, bits = t.path(6)
     nodes = ctx.merkle_paths(bn.fr_to_bytes(vals[6]), sibs, [bits], 20)
     assert nodes[-32:] == t.root()
+    # persistence behind the KvStore-shaped interface: reopen the same store
+    reopened = ob.MerkleTree(ctx, 20, store=t.store)
+    assert reopened.n_leaves == 9 and reopened.root() == t.root() and reopened.path(6) == (sibs, bits)
+    reopened.insert(123)
+    ref.insert(123)
+    assert int.from_bytes(reopened.root(), "little") == ref.root()
+    with pytest.raises(ValueError):
+        ob.MerkleTree(ctx, 19, store=t.store)
     lv = ctx.merkle_build(cport.frs(vals[:8]))
     r8 = mimc7.MerkleTree(3)
     for v in vals[:8]:
