@@ -261,12 +261,13 @@ def test_groth16_golden_proof(ctx):
     PK.close()
 
 
-def test_groth16_prove_bit_exact_vs_oracle(ctx, keys32):
+def test_groth16_prove_bit_exact_vs_oracle(ctx, keys32, monkeypatch):
+    monkeypatch.setenv("OG_CHUNK", "64")         # the 70-proof batch below then spans two chunks of the prover
     pk, vk, cs, pkb, vkb = keys32
     rng = random.Random(12)
     PK = ob.ProvingKey(ctx, pk)
     assert (PK.n_vars, PK.n_pub, PK.log_m, PK.depth) == (cs.n_vars, 3, 15, 32)
-    batch = 70                                   # spans two chunks of the prover (default chunk 64)
+    batch = 70
     nul, sec, rec, sib, bits = rand_inputs(rng, batch, 32)
     rs = cport.frs([rng.randrange(R) for _ in range(2 * batch)])
     wit = cport.withdraw_witness(nul, sec, rec, sib, bits, 32)
