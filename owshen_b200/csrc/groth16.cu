@@ -417,6 +417,15 @@ static int32_t prove_batch(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t 
     return OG_OK;
 }
 
+// offsets into the sorted digit lists and bucket keys are 32-bit: bound the chunk so they cannot overflow
+static uint32_t chunk_limit(const og_pk* pk) {
+    uint64_t max_pts = pk->nC > pk->nA ? pk->nC : pk->nA;
+    uint64_t by_entries = 0xF0000000ull / (max_pts * pk->max_windows);
+    uint64_t by_keys = 0x7FFFFFFFull / pk->max_nb;
+    uint64_t lim = by_entries < by_keys ? by_entries : by_keys;
+    return (uint32_t)(lim < 1 ? 1 : lim);
+}
+
 static uint32_t chunk_size(uint32_t batch) {
     uint32_t c = env_u32("OG_CHUNK", 1024);   // ~28 GB of scratch at 1024 proofs; measured 2037 / 2076 / 2093 proofs/s at 256 / 512 / 1024
     return c < batch ? c : batch;
@@ -430,6 +439,7 @@ int32_t prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_null, 
     WithdrawLayout L = WithdrawLayout::make(pk->depth);
     if (L.n_vars != pk->n_vars) return OG_E_INVALID;
     uint32_t CB = chunk_size(batch);
+    if (CB > chunk_limit(pk)) CB = chunk_limit(pk);
     ChunkBufs b;
     OG_TRY(alloc_chunk(ctx, pk, batch, CB, b));
     OG_TRY(withdraw_witness_strided_dev(ctx, L, b.w_stride, d_null, d_sec, d_rec, d_sib, d_bits, batch, b.W));
@@ -440,6 +450,7 @@ int32_t prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_null, 
 int32_t prove_witness_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_wit, uint32_t batch, const uint8_t* d_rs, uint8_t* d_proofs) {
     if (batch == 0) return OG_OK;
     uint32_t CB = chunk_size(batch);
+    if (CB > chunk_limit(pk)) CB = chunk_limit(pk);
     ChunkBufs b;
     OG_TRY(alloc_chunk(ctx, pk, batch, CB, b));
     uint64_t tot = (uint64_t)batch * pk->n_vars;
