@@ -336,11 +336,23 @@ __global__ void __launch_bounds__(128, MINB) k_bucket_acc(const Affine<F>* __res
         return;
     }
     if (cnt) {
-        Affine<F> nxt = fetch_point(table, sorted[off]);
-        for (uint32_t k = 0; k < cnt; k++) {
-            Affine<F> cur = nxt;
-            if (k + 1 < cnt) nxt = fetch_point(table, sorted[off + k + 1]);   // overlap the gather with the add
-            acc.madd(cur);
+        if constexpr (sizeof(F) == 32) {
+            Affine<F> nxt = fetch_point(table, sorted[off]);
+            for (uint32_t k = 0; k < cnt; k++) {
+                Affine<F> cur = nxt;
+                if (k + 1 < cnt) nxt = fetch_point(table, sorted[off + k + 1]);   // overlap the gather with the add
+                acc.madd(cur);
+            }
+        } else {
+            // G2: a prefetched point costs 32 more live registers in a kernel that already spills; only the
+            // next ENTRY is read ahead, the 128-byte gather is covered by the other warps
+            uint32_t e = sorted[off];
+            for (uint32_t k = 0; k < cnt; k++) {
+                uint32_t en = k + 1 < cnt ? sorted[off + k + 1] : 0;
+                Affine<F> cur = fetch_point(table, e);
+                acc.madd(cur);
+                e = en;
+            }
         }
     }
     buckets[key] = acc;
