@@ -95,3 +95,26 @@ def test_kvstore_shape_matches_reference_trait():
     assert s.get_raw(b"k1") == b"v1" and s.get_raw(b"missing") is None
     s.batch_put_raw([(b"k1", None)])
     assert s.get_raw(b"k1") is None and s.get_raw(b"k2") == b"v2"
+
+
+def test_external_encodings_round_trip():
+    """EIP-197 calldata layout and snarkjs JSON of the library's proof / vk blobs (pure byte shuffling)."""
+    import json
+    from owshen_b200 import formats
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "vectors.json")))["groth16"]
+    proof = bytes.fromhex(g["proof"])
+    ev = formats.proof_to_eip197(proof)
+    assert len(ev) == 256 and formats.proof_from_eip197(ev) == proof
+    (ax, ay), ((bx0, bx1), (by0, by1)), (cx, cy) = formats.proof_points(proof)
+    assert int.from_bytes(ev[:32], "big") == ax and int.from_bytes(ev[64:96], "big") == bx1 and int.from_bytes(ev[96:128], "big") == bx0
+    assert bn.g1_on_curve((ax, ay)) and bn.g1_on_curve((cx, cy)) and bn.g2_on_curve(((bx0, bx1), (by0, by1)))
+    sj = formats.proof_to_snarkjs(proof)
+    assert sj["pi_a"] == [str(ax), str(ay), "1"] and sj["pi_b"][0] == [str(bx0), str(bx1)]
+    v = g["vk"]
+    vk = b"OGVK" + (1).to_bytes(4, "little") + (3).to_bytes(4, "little") + bytes.fromhex(v["alpha1"] + v["beta2"] + v["gamma2"] + v["delta2"] + v["ic"])
+    p = formats.parse_vk(vk)
+    assert p["n_pub"] == 3 and len(p["ic"]) == 4 and all(bn.g1_on_curve(q) for q in p["ic"]) and bn.g2_on_curve(p["delta2"])
+    assert formats.vk_to_snarkjs(vk)["nPublic"] == 3
+    pub = b"".join(bn.fr_to_bytes(int(x)) for x in g["public"])
+    assert formats.public_inputs_to_eip197(pub)[:32] == int(g["public"][0]).to_bytes(32, "big")
+    assert ob.verify(vk, pub, proof)
