@@ -115,3 +115,29 @@ def test_lazy_fq2_product_extremes(h):
     for a, b in cases:
         h.ht_fq2_mul(cport.fqs(a), cport.fqs(b), o)
         assert tuple(cport.unfr(o.raw)) == bn.f2_mul(a, b), (a, b)
+
+
+def test_field_limbs_hypothesis(h):
+    """Property test with boundary-biased operands: limb carries are where Montgomery code breaks."""
+    from hypothesis import given, settings, strategies as st
+
+    def elems(mod):
+        edges = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, 2**32 - 1, 2**32, 2**64 - 1, 2**128, 2**224 - 1, 2**253, 2**253 + 2**32 - 1]
+        limbs = st.lists(st.sampled_from([0, 1, 0xFFFFFFFF, 0xFFFFFFFE, 0x80000000, 0x7FFFFFFF]) | st.integers(0, 2**32 - 1), min_size=8, max_size=8)
+        from_limbs = limbs.map(lambda l: sum(v << (32 * i) for i, v in enumerate(l)) % mod)
+        return st.sampled_from([e % mod for e in edges]) | from_limbs | st.integers(0, mod - 1)
+
+    for F, mod, pack in (("fq", P, cport.fqs), ("fr", R, cport.frs)):
+        @settings(max_examples=300, deadline=None)
+        @given(st.lists(st.tuples(elems(mod), elems(mod)), min_size=1, max_size=20))
+        def check(pairs):
+            xs = [a for a, _ in pairs]; ys = [b for _, b in pairs]
+            assert cport.unfr(_binop(h, f"ht_{F}_mul", pack(xs), pack(ys))) == [a * b % mod for a, b in pairs]
+            assert cport.unfr(_binop(h, f"ht_{F}_add", pack(xs), pack(ys))) == [(a + b) % mod for a, b in pairs]
+            assert cport.unfr(_binop(h, f"ht_{F}_sub", pack(xs), pack(ys))) == [(a - b) % mod for a, b in pairs]
+            if F == "fq":
+                n = len(xs)
+                m = C.create_string_buffer(32 * n); s = C.create_string_buffer(32 * n)
+                h.ht_wide(pack(xs), pack(ys), m, s, C.c_uint64(n))
+                assert cport.unfr(m.raw) == [a * b % mod for a, b in pairs] and cport.unfr(s.raw) == [a * a % mod for a in xs]
+        check()
