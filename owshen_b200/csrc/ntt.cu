@@ -14,6 +14,7 @@
 // One table per size serves everything: T2[j] = omega_{2n}^j (j < n): coset factors are T2[j],
 // stage twiddles are omega_n^e = T2[2e], inverses are -T2[n - j].
 #include "ntt.cuh"
+#include <stdlib.h>
 
 namespace og {
 
@@ -108,6 +109,111 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassPlan P, const Fr* __restri
     }
 }
 
+// ---- version 2 of the pass kernel -----------------------------------------------------------------------
+// Same pass plan, three changes taken from the ncu capture of k_ntt_pass (profiles/): (1) two butterfly levels per
+// barrier with the four operands in registers (half the shared-memory round trips and barriers); (2) the 32-byte
+// elements are stored as two 16-byte chunks whose position is XOR-swizzled with bit 2 of the element index, which
+// removes the 2-way bank conflict of the plain array-of-structures layout (58 % of the wavefronts were replays);
+// (3) the first level of the first pass has twiddle 1 everywhere and skips its products.
+__device__ __forceinline__ uint32_t sw_chunk(uint32_t e, uint32_t h) { return ((e << 1) | h) ^ ((e >> 2) & 1); }
+__device__ __forceinline__ Fr sm_get(const uint4* sm, uint32_t e) {
+    uint4 a = sm[sw_chunk(e, 0)], b = sm[sw_chunk(e, 1)];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sm_put(uint4* sm, uint32_t e, const Fr& v) {
+    sm[sw_chunk(e, 0)] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    sm[sw_chunk(e, 1)] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+__global__ void __launch_bounds__(256) k_ntt_pass2(PassPlan P, const Fr* __restrict__ in, Fr* __restrict__ out,
+                                                   const Fr* __restrict__ t2, Fr n_inv) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    uint4* sm = reinterpret_cast<uint4*>(smem_raw);
+    const uint32_t n = 1u << P.log_n;
+    const uint32_t B0 = P.s0 - 1;
+    const uint32_t tile = 1u << (P.K + P.L);
+    const uint32_t t = blockIdx.x;
+    const uint32_t mid = t & ((1u << (B0 - P.L)) - 1), top = t >> (B0 - P.L);
+    const uint32_t base = (top << (B0 + P.K)) | (mid << P.L);
+    const Fr* src = in + (size_t)blockIdx.y * n;
+    Fr* dst = out + (size_t)blockIdx.y * n;
+    const uint32_t lmask = (1u << P.L) - 1;
+
+    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
+        uint32_t lo = e & lmask, k = e >> P.L;
+        uint32_t i = base | (k << B0) | lo;
+        Fr v;
+        if (P.first) {
+            uint32_t j = bitrev(i, P.log_n);
+            v = src[j];
+            if (P.coset && !P.inverse) v = v * t2[j];
+        } else {
+            v = src[i];
+        }
+        sm_put(sm, e, v);
+    }
+    __syncthreads();
+
+    uint32_t q = 1;
+    for (; q + 1 <= P.K; q += 2) {                      // two levels per barrier
+        const uint32_t s = P.s0 + q - 1;
+        const bool unit = P.first && q == 1;            // all twiddles of level 1 (and w2a of level 2) are omega^0
+        for (uint32_t g = threadIdx.x; g < (tile >> 2); g += blockDim.x) {
+            uint32_t lo = g & lmask, kb = g >> P.L;
+            uint32_t klow = kb & ((1u << (q - 1)) - 1), khigh = kb >> (q - 1);
+            uint32_t k00 = (khigh << (q + 1)) | klow;
+            uint32_t e00 = (k00 << P.L) | lo, d1 = (1u << (q - 1)) << P.L, d2 = (1u << q) << P.L;
+            uint32_t j1 = (klow << B0) | (mid << P.L) | lo;                       // < 2^(s-1)
+            uint32_t j2b = j1 + (1u << (q - 1 + B0));                             // < 2^s
+            Fr x00 = sm_get(sm, e00), x01 = sm_get(sm, e00 + d1), x10 = sm_get(sm, e00 + d2), x11 = sm_get(sm, e00 + d1 + d2);
+            Fr a0, a1, b0, b1;
+            if (unit) {
+                a0 = x00 + x01; a1 = x00 - x01; b0 = x10 + x11; b1 = x10 - x11;
+            } else {
+                Fr w1 = tw2(t2, n, j1 << (P.log_n + 1 - s), P.inverse);
+                Fr u = x01 * w1, v = x11 * w1;
+                a0 = x00 + u; a1 = x00 - u; b0 = x10 + v; b1 = x10 - v;
+            }
+            Fr w2b = tw2(t2, n, j2b << (P.log_n - s), P.inverse);
+            Fr p0 = unit ? b0 : b0 * tw2(t2, n, j1 << (P.log_n - s), P.inverse);
+            Fr p1 = b1 * w2b;
+            sm_put(sm, e00, a0 + p0);
+            sm_put(sm, e00 + d2, a0 - p0);
+            sm_put(sm, e00 + d1, a1 + p1);
+            sm_put(sm, e00 + d1 + d2, a1 - p1);
+        }
+        __syncthreads();
+    }
+    if (q <= P.K) {                                      // odd number of levels: one plain level
+        const uint32_t s = P.s0 + q - 1;
+        for (uint32_t b = threadIdx.x; b < (tile >> 1); b += blockDim.x) {
+            uint32_t lo = b & lmask, kb = b >> P.L;
+            uint32_t klow = kb & ((1u << (q - 1)) - 1);
+            uint32_t k0 = ((kb >> (q - 1)) << q) | klow;
+            uint32_t e0 = (k0 << P.L) | lo, e1 = e0 + ((1u << (q - 1)) << P.L);
+            uint32_t j = (klow << B0) | (mid << P.L) | lo;
+            Fr u = sm_get(sm, e0);
+            Fr v = (P.first && q == 1) ? sm_get(sm, e1) : sm_get(sm, e1) * tw2(t2, n, j << (P.log_n + 1 - s), P.inverse);
+            sm_put(sm, e0, u + v);
+            sm_put(sm, e1, u - v);
+        }
+        __syncthreads();
+    }
+
+    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
+        uint32_t lo = e & lmask, k = e >> P.L;
+        uint32_t i = base | (k << B0) | lo;
+        Fr v = sm_get(sm, e);
+        if (P.last && P.inverse) {
+            v = v * n_inv;
+            if (P.coset) v = v * tw2(t2, n, i, true);
+        }
+        dst[i] = v;
+    }
+}
+
 static int32_t get_tables(og_ctx* ctx, uint32_t log_n, NttTables** out) {
     if (log_n > 27) return OG_E_INVALID;
     if (!ctx->ntt[log_n]) {
@@ -172,9 +278,17 @@ int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t ba
         Fr* dst = (i == np - 1) ? data : tmp;
         if (np == 1) { src = data; dst = data; }
         uint32_t tile = 1u << (p.K + p.L);
-        uint32_t threads = tile / 2 < 32 ? 32 : (tile / 2 > 512 ? 512 : tile / 2);
         dim3 grid((1u << log_n) / tile, batch);
-        OG_LAUNCH(ctx, k_ntt_pass, grid, threads, tile * sizeof(Fr), p, src, dst, T->d_t2, T->n_inv);
+        static const int v1 = [] { const char* e = getenv("OG_NTT_V1"); return e ? atoi(e) : 0; }();
+        if (v1) {
+            uint32_t threads = tile / 2 < 32 ? 32 : (tile / 2 > 512 ? 512 : tile / 2);
+            OG_LAUNCH(ctx, k_ntt_pass, grid, threads, tile * sizeof(Fr), p, src, dst, T->d_t2, T->n_inv);
+        } else {
+            uint32_t threads = tile / 4 < 32 ? 32 : (tile / 4 > 256 ? 256 : tile / 4);
+            // the swizzle permutes chunks inside groups of 8 elements: pad tiny tiles up to one group
+            size_t smem = (tile < 8 ? 8 : tile) * sizeof(Fr);
+            OG_LAUNCHN(ctx, "k_ntt_pass", k_ntt_pass2, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv);
+        }
     }
     return OG_OK;
 }
