@@ -111,9 +111,9 @@ def test_merkle_tree_api(ctx):
 
 def test_ntt_matches_oracle_all_modes(ctx):
     rng = random.Random(5)
-    for log_n in (0, 1, 2, 3, 7, 10, 11, 12, 15, 16):
+    for log_n in (0, 1, 2, 3, 7, 10, 11, 12, 13, 14, 15, 16, 17):     # every parity of levels per pass
         n = 1 << log_n
-        batch = 3 if log_n <= 12 else 2
+        batch = 3 if log_n <= 12 else (2 if log_n <= 16 else 1)
         data = rand_fr_bytes(rng, n * batch)
         for inv in (False, True):
             for co in (False, True):
