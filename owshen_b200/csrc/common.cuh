@@ -33,6 +33,7 @@ struct og_ctx {
     og::NttTables* ntt[32] = {nullptr};
     void* g1_fixed = nullptr;        // fixed-base tables of the generators (setup only)
     void* g2_fixed = nullptr;
+    bool sort_smem_opt_in = false;   // cudaFuncSetAttribute(k_sort_group) done for this device
     bool digits_smem_opt_in = false; // cudaFuncSetAttribute(k_digits_tiled) done for this device
 
     // optional per-kernel timing: CUDA events around every launch of this library (og_profile)
