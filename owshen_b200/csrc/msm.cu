@@ -452,7 +452,9 @@ constexpr uint32_t RED_FAN_LOG2 = 3, RED_FAN = 1u << RED_FAN_LOG2;   // 8 childr
 // Element e of a level carries S_e (plain sum of the buckets under e) and U_e (their 0-based weighted sum
 // relative to e's first bucket).  Merging children c_0..c_k, each covering 2^w_log2 buckets:
 //   S_p = sum S_c;   U_p = sum U_c + 2^w_log2 * sum_c idx(c) * S_c   (running-sum trick for the last term).
-template <class F>
+// HAS_U = false is level 0 (children are raw buckets, no weighted part yet): most of the work, and one 4-coordinate
+// accumulator fewer to keep in registers.
+template <class F, bool HAS_U>
 __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
                                                      uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
                                                      XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ U_out) {
@@ -460,22 +462,22 @@ __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__
     if (t >= n_groups * n_out) return;
     uint32_t g = t / n_out, p = t % n_out;
     const XYZZ<F>* S = S_in + (size_t)g * n_in;
-    const XYZZ<F>* U = U_in ? U_in + (size_t)g * n_in : nullptr;
     uint32_t lo = p * RED_FAN, hi = min(n_in, lo + RED_FAN);
     // group operations inlined here: with 2^15 buckets per proof this kernel is 10 % of a proving step, and the
     // out-of-line versions move every operand through local memory
-    XYZZ<F> R = XYZZ<F>::inf(), T = XYZZ<F>::inf(), Us = XYZZ<F>::inf();
+    XYZZ<F> R = XYZZ<F>::inf(), T = XYZZ<F>::inf();
     for (uint32_t i = hi - 1; i > lo; i--) {
         R.add(S[i]);
         T.add(R);
-        if (U) Us.add(U[i]);
     }
     R.add(S[lo]);
-    if (U) Us.add(U[lo]);
     for (uint32_t k = 0; k < w_log2; k++) T = T.dbl();
-    Us.add(T);
+    if (HAS_U) {
+        const XYZZ<F>* U = U_in + (size_t)g * n_in;
+        for (uint32_t i = lo; i < hi; i++) T.add(U[i]);
+    }
     S_out[(size_t)g * n_out + p] = R;
-    U_out[(size_t)g * n_out + p] = Us;
+    U_out[(size_t)g * n_out + p] = T;
 }
 
 // total_g = U_g + S_g   (weights are b+1)
@@ -527,7 +529,9 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     do {
         uint32_t n_out = (n_in + RED_FAN - 1) / RED_FAN;
         uint32_t threads = n_groups * n_out;
-        OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2", k_reduce_level<F>, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]);
+        const char* rn = sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2";
+        if (U_in) { auto k = k_reduce_level<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]); }
+        else { auto k = k_reduce_level<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]); }
         S_in = bufS[pp]; U_in = bufU[pp];
         pp ^= 1;
         n_in = n_out;
