@@ -72,6 +72,9 @@ int32_t og_int_pipe_peaks(og_ctx* ctx, double* mad_per_s, double* wide_mad_per_s
 /* SM cycles per dependent Fr multiply(+add) for one warp alone on a scheduler, and per iteration of two
  * independent chains: the latency that bounds the sequential MiMC chains (planning probe) */
 int32_t og_mul_latency(og_ctx* ctx, double* cycles_dependent, double* cycles_two_chains);
+/* planning probe for a hybrid multiplier: rates4 = {52x52-bit FP64-pipe products/s alone, 32x32-bit carry-chain
+ * multiply-adds/s alone, and both rates when the two kinds run interleaved in every warp} */
+int32_t og_hybrid_probe(og_ctx* ctx, double* rates4);
 /* FP64 fused multiply-adds per second (planning probe: the FP64 pipe is idle in every kernel of this library) */
 int32_t og_fp64_peak(og_ctx* ctx, double* dfma_per_s);
 

@@ -48,6 +48,7 @@ _SIGS = {
     "og_imad_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "og_int_pipe_peaks": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "og_mul_latency": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "og_hybrid_probe": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     "og_fp64_peak": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double)]),
     "og_field_op": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_mimc7_constants": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint32)]),
@@ -185,6 +186,12 @@ class Context:
         a, b = C.c_double(), C.c_double()
         _check(lib().og_mul_latency(self._h, C.byref(a), C.byref(b)), self)
         return a.value, b.value
+
+    def hybrid_probe(self) -> dict:
+        r = (C.c_double * 4)()
+        _check(lib().og_hybrid_probe(self._h, r), self)
+        return {"fp64_products_52bit_alone": r[0], "imad_wide_chain_alone": r[1],
+                "fp64_products_52bit_mixed": r[2], "imad_wide_chain_mixed": r[3]}
 
     def fp64_peak(self) -> float:
         v = C.c_double()

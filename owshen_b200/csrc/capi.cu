@@ -286,9 +286,91 @@ __global__ void __launch_bounds__(256) k_dfma(double* out, uint32_t iters, doubl
     if (s == 1.2345) out[0] = s;
 }
 
+// Hybrid-multiplier probe (round-2 planning).  A 52x52-bit product on the FP64 pipe costs two DFMA, one DADD and
+// two 64-bit integer adds (Emmart et al.: hi = fma_rz(a, b, 2^104), lo = fma_rz(a, b, 2^104 + 2^52 - hi), the bit
+// patterns accumulate as integers).  MODE 0: those products alone; MODE 1: the carry-chain IMAD.WIDE rows alone;
+// MODE 2: both interleaved in every warp -- does the chip run the two multipliers at the same time?
+template <int MODE>
+__global__ void __launch_bounds__(256) k_hybrid(unsigned long long* out, uint32_t iters, uint32_t seed) {
+    const double C1 = 20282409603651670423947251286016.0;                  // 2^104
+    const double C2 = 20282409603651670423947251286016.0 + 4503599627370496.0;   // 2^104 + 2^52
+    double a[4], b[4];
+    long long acc_hi[4] = {0, 0, 0, 0}, acc_lo[4] = {0, 0, 0, 0};
+    uint32_t e[8], o[8];
+    uint32_t x = blockIdx.x * 2654435761u + 12345u + seed, y = x ^ 0x9e3779b9u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { a[k] = (double)((threadIdx.x * 977u + k * 131u + seed) & 0xFFFFF) + 4503599627370.0; b[k] = a[k] * 0.5 + 7.0; }
+#pragma unroll
+    for (int k = 0; k < 8; k++) { e[k] = threadIdx.x * (2 * k + 3) + seed; o[k] = e[k] ^ y; }
+    CC cc;
+    for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (MODE == 0 || MODE == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {                                 // 4 products of 52 x 52 bits
+                    double hi = __fma_rz(a[k], b[(k + r) & 3], C1);
+                    double sub = C2 - hi;
+                    double lo = __fma_rz(a[k], b[(k + r) & 3], sub);
+                    acc_hi[k] += __double_as_longlong(hi);
+                    acc_lo[k] += __double_as_longlong(lo);
+                }
+                a[r] = a[r] + 1.0;                                            // keep the products loop-variant
+            }
+            if (MODE == 1 || MODE == 2) {                                     // 8 products of 32 x 32 -> 64 bits (lo and hi halves fuse)
+                uint32_t m0 = e[7] | 1u, m1 = o[7] | 1u;
+                e[0] = mad_lo_cc(m0, x, e[0], cc); e[1] = madc_hi_cc(m0, x, e[1], cc);
+                e[2] = madc_lo_cc(m0, y, e[2], cc); e[3] = madc_hi_cc(m0, y, e[3], cc);
+                e[4] = madc_lo_cc(m0, x, e[4], cc); e[5] = madc_hi_cc(m0, x, e[5], cc);
+                e[6] = madc_lo_cc(m0, y, e[6], cc); e[7] = madc_hi(m0, y, e[7], cc);
+                o[0] = mad_lo_cc(m1, x, o[0], cc); o[1] = madc_hi_cc(m1, x, o[1], cc);
+                o[2] = madc_lo_cc(m1, y, o[2], cc); o[3] = madc_hi_cc(m1, y, o[3], cc);
+                o[4] = madc_lo_cc(m1, x, o[4], cc); o[5] = madc_hi_cc(m1, x, o[5], cc);
+                o[6] = madc_lo_cc(m1, y, o[6], cc); o[7] = madc_hi(m1, y, o[7], cc);
+            }
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) s ^= (unsigned long long)acc_hi[k] ^ (unsigned long long)acc_lo[k];
+#pragma unroll
+    for (int k = 0; k < 8; k++) s ^= e[k] ^ o[k];
+    if (s == 0x1234567ull) out[0] = s;
+}
+
 }  // namespace og
 
 extern "C" {
+
+// rates[0] = 52x52 FP64-pipe products/s alone, rates[1] = 32x32->64 carry-chain IMAD.WIDE/s alone,
+// rates[2], rates[3] = the same two rates when both run interleaved in every warp
+int32_t og_hybrid_probe(og_ctx* ctx, double* rates4) {
+    OG_ENTER(ctx);
+    if (!rates4) return OG_E_INVALID;
+    OG_SLOT(ctx, d_out, unsigned long long, S_IO_A, 64);
+    const uint32_t iters = 1024, ctas = ctx->sm_count * 8, threads = 256;
+    const double lanes = (double)ctas * threads * iters * 4.0;        // 4 rounds per iteration
+    float ms[3] = {0, 0, 0};
+    for (int mode = 0; mode < 3; mode++) {
+        float best = 1e30f, t = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            OG_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+            if (mode == 0) OG_LAUNCH(ctx, k_hybrid<0>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
+            else if (mode == 1) OG_LAUNCH(ctx, k_hybrid<1>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
+            else OG_LAUNCH(ctx, k_hybrid<2>, ctas, threads, 0, d_out, iters, (uint32_t)rep);
+            OG_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+            OG_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+            OG_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev0, ctx->ev1));
+            if (rep > 0 && t < best) best = t;
+        }
+        ms[mode] = best;
+    }
+    rates4[0] = lanes * 4.0 / (ms[0] * 1e-3);
+    rates4[1] = lanes * 8.0 / (ms[1] * 1e-3);      // lo+hi of one product fuse into one IMAD.WIDE
+    rates4[2] = lanes * 4.0 / (ms[2] * 1e-3);
+    rates4[3] = lanes * 8.0 / (ms[2] * 1e-3);
+    return OG_OK;
+}
 
 int32_t og_mul_latency(og_ctx* ctx, double* cycles_dependent, double* cycles_two_chains) {
     OG_ENTER(ctx);

@@ -71,3 +71,96 @@ def vk_to_snarkjs(vk: bytes) -> dict:
 
 def to_json(obj: dict) -> str:
     return json.dumps(obj, indent=1)
+
+
+# ---- the node's transaction envelope ------------------------------------------------------
+# /root/reference/src/types/tx/custom.rs:214-256 wraps every custom message as an RLP list whose first item is the
+# message kind as a string ("mint", "burn"), byte fields following as RLP strings, integers as little-endian byte
+# vectors (custom.rs:40, `amount.as_le_bytes()`).  A shielded withdrawal carrying one of this library's proofs takes
+# the same shape:   ["shielded-withdraw", proof (256 B), root, nullifier_hash, recipient (32 B LE each)].
+# RLP itself is the Ethereum yellow-paper appendix B encoding (crate `rlp` 0.5.2 in the reference's Cargo.toml:13).
+
+SHIELDED_WITHDRAW_KIND = "shielded-withdraw"
+
+
+def rlp_encode(item) -> bytes:
+    """RLP of bytes / str / list (nested).  Integers are not accepted: the reference passes them as LE byte vectors."""
+    if isinstance(item, str):
+        item = item.encode()
+    if isinstance(item, (bytes, bytearray)):
+        b = bytes(item)
+        if len(b) == 1 and b[0] < 0x80:
+            return b
+        return _rlp_len(len(b), 0x80) + b
+    if isinstance(item, (list, tuple)):
+        body = b"".join(rlp_encode(x) for x in item)
+        return _rlp_len(len(body), 0xC0) + body
+    raise TypeError(f"rlp_encode: unsupported {type(item).__name__}")
+
+
+def _rlp_len(n: int, base: int) -> bytes:
+    if n < 56:
+        return bytes([base + n])
+    nb = n.to_bytes((n.bit_length() + 7) // 8, "big")
+    return bytes([base + 55 + len(nb)]) + nb
+
+
+def rlp_decode(data: bytes):
+    """Inverse of rlp_encode (strings come back as bytes).  Rejects trailing bytes and non-minimal lengths, like the
+    reference's decoder returning DecoderError (custom.rs:176-183 maps those to a rejected transaction)."""
+    item, end = _rlp_item(bytes(data), 0)
+    if end != len(data):
+        raise ValueError("rlp: trailing bytes")
+    return item
+
+
+def _rlp_item(d: bytes, i: int):
+    if i >= len(d):
+        raise ValueError("rlp: truncated")
+    t = d[i]
+    if t < 0x80:
+        return d[i:i + 1], i + 1
+    is_list = t >= 0xC0
+    base = 0xC0 if is_list else 0x80
+    if t - base < 56:
+        n, start = t - base, i + 1
+        if not is_list and n == 1 and start < len(d) and d[start] < 0x80:
+            raise ValueError("rlp: single byte below 0x80 must be encoded as itself")
+    else:
+        ln = t - base - 55
+        if i + 1 + ln > len(d) or d[i + 1] == 0:
+            raise ValueError("rlp: bad length prefix")
+        n, start = int.from_bytes(d[i + 1:i + 1 + ln], "big"), i + 1 + ln
+        if n < 56:
+            raise ValueError("rlp: non-minimal length")
+    if start + n > len(d):
+        raise ValueError("rlp: truncated")
+    if not is_list:
+        return d[start:start + n], start + n
+    out, j = [], start
+    while j < start + n:
+        x, j = _rlp_item(d, j)
+        out.append(x)
+    if j != start + n:
+        raise ValueError("rlp: list overruns its length")
+    return out, j
+
+
+def shielded_withdraw_to_rlp(proof: bytes, public_inputs: bytes) -> bytes:
+    """CustomTxMsg-shaped message for one withdraw proof: public_inputs = root || nullifier_hash || recipient (96 B,
+    the `public_out` row of og_groth16_prove_withdraw)."""
+    if len(proof) != 256 or len(public_inputs) != 96:
+        raise ValueError("shielded_withdraw_to_rlp: proof must be 256 bytes, public inputs 96")
+    return rlp_encode([SHIELDED_WITHDRAW_KIND, proof, public_inputs[0:32], public_inputs[32:64], public_inputs[64:96]])
+
+
+def shielded_withdraw_from_rlp(msg: bytes):
+    """-> (proof, public_inputs); raises ValueError on anything that is not a well-formed shielded-withdraw message
+    (the reference's from_rlp answers `Err(anyhow!("Invalid tx!"))` for an unknown kind, custom.rs:253)."""
+    item = rlp_decode(msg)
+    if not isinstance(item, list) or len(item) != 5 or any(isinstance(x, list) for x in item):
+        raise ValueError("Invalid tx!")
+    kind, proof, root, nh, rcpt = item
+    if kind != SHIELDED_WITHDRAW_KIND.encode() or len(proof) != 256 or any(len(x) != 32 for x in (root, nh, rcpt)):
+        raise ValueError("Invalid tx!")
+    return proof, root + nh + rcpt

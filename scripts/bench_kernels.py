@@ -70,6 +70,8 @@ def main():
     pipes = ctx.int_pipe_peaks()
     print(json.dumps({"kernel": "int_pipe_peaks", **pipes, "note": "multiply-adds per second; carry-chain figure is the Montgomery-row shape"}), flush=True)
     print(json.dumps({"kernel": "fp64_peak", "dfma_per_s": ctx.fp64_peak(), "note": "FP64 pipe is idle in every kernel of this library (planning probe)"}), flush=True)
+    print(json.dumps({"kernel": "hybrid_probe", **ctx.hybrid_probe(),
+                      "note": "52x52-bit products on the FP64 pipe vs 32x32-bit carry-chain IMAD.WIDE, alone and interleaved (round-2 planning)"}), flush=True)
     wide_peak = pipes["imad_wide_carry_chain_per_s"]
     flush = torch.zeros(256 << 20, dtype=torch.uint8, device=device)    # 256 MB > L2
 
