@@ -17,7 +17,7 @@ _lib = None
 FR_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 PROOF_BYTES = 256
 
-OG_OK, OG_E_VERIFY = 0, -6
+OG_OK, OG_E_INVALID, OG_E_VERIFY = 0, -1, -6
 
 
 class OwshenB200Error(RuntimeError):

@@ -60,6 +60,15 @@ int32_t check_flag(og_ctx* ctx) {
         OG_CUDA(ctx, cudaSetDevice((ctx)->device));                                                \
     } while (0)
 
+// a proving key's tables are device memory of the GPU it was loaded on: refuse it on any other context's GPU
+#define OG_PK_CHECK(ctx, pk)                                                                           \
+    do {                                                                                               \
+        if (!pk_on_device_of(pk, ctx)) {                                                               \
+            snprintf((ctx)->err, sizeof((ctx)->err), "proving key was loaded on another device");      \
+            return OG_E_INVALID;                                                                       \
+        }                                                                                              \
+    } while (0)
+
 #define H2D(ctx, dst, src, bytes) OG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (ctx)->stream))
 #define D2H(ctx, dst, src, bytes) OG_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (ctx)->stream))
 
@@ -719,6 +728,7 @@ int32_t og_pk_info(const og_pk* pk, uint32_t* n_vars, uint32_t* n_pub, uint32_t*
 int32_t og_groth16_prove(og_ctx* ctx, const og_pk* pk, const uint8_t* witnesses, uint32_t batch, const uint8_t* rs, uint8_t* proofs) {
     OG_ENTER(ctx);
     if (!ctx || !pk || !witnesses || !rs || !proofs) return OG_E_INVALID;
+    OG_PK_CHECK(ctx, pk);
     if (batch == 0) return OG_OK;
     uint32_t nv; pk_info(pk, &nv, nullptr, nullptr, nullptr);
     OG_SLOT(ctx, dw, uint8_t, S_IO_A, 32ull * batch * nv);
@@ -736,6 +746,7 @@ int32_t og_groth16_prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_
                                       const uint8_t* d_rs, uint8_t* d_proofs, uint8_t* d_public_out) {
     OG_ENTER(ctx);
     if (!ctx || !pk || !d_nullifiers || !d_secrets || !d_recipients || !d_siblings || !d_path_bits || !d_rs || !d_proofs) return OG_E_INVALID;
+    OG_PK_CHECK(ctx, pk);
     return prove_withdraw_dev(ctx, pk, d_nullifiers, d_secrets, d_recipients, d_siblings, d_path_bits, batch, d_rs, d_proofs, d_public_out);
 }
 
@@ -744,6 +755,7 @@ int32_t og_groth16_prove_withdraw(og_ctx* ctx, const og_pk* pk, const uint8_t* n
                                   uint8_t* public_out) {
     OG_ENTER(ctx);
     if (!ctx || !pk || !nullifiers || !secrets || !recipients || !siblings || !path_bits || !rs || !proofs) return OG_E_INVALID;
+    OG_PK_CHECK(ctx, pk);
     if (batch == 0) return OG_OK;
     uint32_t depth, n_pub; pk_info(pk, nullptr, &n_pub, nullptr, &depth);
     if (depth == 0) return OG_E_INVALID;
@@ -767,6 +779,7 @@ int32_t og_groth16_prove_withdraw(og_ctx* ctx, const og_pk* pk, const uint8_t* n
 int32_t og_groth16_h_evals(og_ctx* ctx, const og_pk* pk, const uint8_t* witness, uint8_t* out) {
     OG_ENTER(ctx);
     if (!ctx || !pk || !witness || !out) return OG_E_INVALID;
+    OG_PK_CHECK(ctx, pk);
     uint32_t nv, log_m; pk_info(pk, &nv, nullptr, &log_m, nullptr);
     OG_SLOT(ctx, dw, uint8_t, S_IO_A, 32ull * nv);
     OG_SLOT(ctx, dout, uint8_t, S_IO_B, 32ull << log_m);

@@ -313,6 +313,8 @@ int32_t pk_load(og_ctx* ctx, const uint8_t* bytes, uint64_t len, og_pk** out) {
     return OG_OK;
 }
 
+bool pk_on_device_of(const og_pk* pk, const og_ctx* ctx) { return pk && ctx && pk->ctx && pk->ctx->device == ctx->device; }
+
 void pk_info(const og_pk* pk, uint32_t* n_vars, uint32_t* n_pub, uint32_t* log_m, uint32_t* depth) {
     if (n_vars) *n_vars = pk->n_vars;
     if (n_pub) *n_pub = pk->n_pub;

@@ -7,6 +7,8 @@ struct og_pk;
 namespace og {
 int32_t pk_load(og_ctx* ctx, const uint8_t* bytes, uint64_t len, og_pk** out);
 void pk_free(og_pk* pk);
+// true iff the key's tables live on the device `ctx` runs on (a key is bound to the device of the ctx that loaded it)
+bool pk_on_device_of(const og_pk* pk, const og_ctx* ctx);
 void pk_info(const og_pk* pk, uint32_t* n_vars, uint32_t* n_pub, uint32_t* log_m, uint32_t* depth);
 int32_t prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_null, const uint8_t* d_sec, const uint8_t* d_rec,
                            const uint8_t* d_sib, const uint32_t* d_bits, uint32_t batch, const uint8_t* d_rs, uint8_t* d_proofs,

@@ -321,5 +321,14 @@ def test_two_contexts_in_one_process(ctx):
             assert c1.msm_g1(pts, sc) == exp
         x, y = cport.frs([3, 5]), cport.frs([7, 11])
         assert c1.mimc7_hash2(x, y) == ctx.mimc7_hash2(x, y)
+        # a proving key is bound to the GPU that loaded it: another context's GPU must refuse it, not fault
+        pk_bytes, _ = ob.setup_withdraw(ctx, 2, 11, 12, 13, 14, 15)
+        PK = ob.ProvingKey(ctx, pk_bytes)
+        PK.ctx = c1
+        with pytest.raises(ob.OwshenB200Error) as e:
+            PK.prove_withdraw(cport.frs([1]), cport.frs([2]), cport.frs([3]), cport.frs([1, 2]), [0], cport.frs([1, 2]))
+        assert e.value.code == api.OG_E_INVALID and "another device" in str(e.value)
+        PK.ctx = ctx
+        PK.close()
     finally:
         c1.close()
