@@ -457,12 +457,12 @@ constexpr uint32_t RED_FAN_LOG2 = 3, RED_FAN = 1u << RED_FAN_LOG2;   // 8 childr
 template <class F, bool HAS_U>
 __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
                                                      uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
-                                                     XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ U_out) {
+                                                     uint32_t fan_log2, XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ U_out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_groups * n_out) return;
     uint32_t g = t / n_out, p = t % n_out;
     const XYZZ<F>* S = S_in + (size_t)g * n_in;
-    uint32_t lo = p * RED_FAN, hi = min(n_in, lo + RED_FAN);
+    uint32_t lo = p << fan_log2, hi = min(n_in, lo + (1u << fan_log2));
     // group operations inlined here: with 2^15 buckets per proof this kernel is 10 % of a proving step, and the
     // out-of-line versions move every operand through local memory
     XYZZ<F> R = XYZZ<F>::inf(), T = XYZZ<F>::inf();
@@ -504,7 +504,7 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     uint64_t avg = n_entries_max / (n_keys ? n_keys : 1);
     uint32_t cap = (uint32_t)(4 * avg < 128 ? 128 : 4 * avg);
     {
-        static const int occ = [] { const char* v = getenv("OG_ACC_OCC"); return v ? atoi(v) : 0; }();
+        static const int occ = [] { const char* v = getenv(sizeof(F) == 32 ? "OG_ACC_OCC" : "OG_ACC_OCC_G2"); return v ? atoi(v) : 0; }();
         const char* kn = sizeof(F) == 32 ? "k_bucket_acc_g1" : "k_bucket_acc_g2";
         unsigned grid = (n_keys + 127) / 128;
         if constexpr (sizeof(F) == 32) {
@@ -513,6 +513,7 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
             else { auto k = k_bucket_acc<F, 5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
         } else {
             if (occ == 2) { auto k = k_bucket_acc<F, 2>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 4) { auto k = k_bucket_acc<F, 4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
             else { auto k = k_bucket_acc<F, 3>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
         }
     }
@@ -526,16 +527,20 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     const XYZZ<F>* U_in = nullptr;
     uint32_t n_in = nb, w_log2 = 0;
     int pp = 0;
+    // level 0 (raw buckets) is most of the work: a wider fan there spends fewer additions per bucket (2 - 1/fan)
+    // and leaves less for the levels above, at the price of longer serial chains; OG_RED_FAN0 = 3, 4 or 5
+    static const uint32_t fan0 = [] { const char* v = getenv("OG_RED_FAN0"); int x = v ? atoi(v) : 0; return (uint32_t)(x >= 3 && x <= 5 ? x : RED_FAN_LOG2); }();
     do {
-        uint32_t n_out = (n_in + RED_FAN - 1) / RED_FAN;
+        uint32_t fan_log2 = U_in ? RED_FAN_LOG2 : fan0;
+        uint32_t n_out = (n_in + (1u << fan_log2) - 1) >> fan_log2;
         uint32_t threads = n_groups * n_out;
         const char* rn = sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2";
-        if (U_in) { auto k = k_reduce_level<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]); }
-        else { auto k = k_reduce_level<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, bufS[pp], bufU[pp]); }
+        if (U_in) { auto k = k_reduce_level<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+        else { auto k = k_reduce_level<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
         S_in = bufS[pp]; U_in = bufU[pp];
         pp ^= 1;
         n_in = n_out;
-        w_log2 += RED_FAN_LOG2;
+        w_log2 += fan_log2;
     } while (n_in > 1);
     OG_LAUNCH(ctx, k_group_total<F>, (n_groups + 63) / 64, 64, 0, S_in, U_in, n_groups, d_totals);
     return OG_OK;
