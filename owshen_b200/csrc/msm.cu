@@ -424,6 +424,72 @@ __global__ void __launch_bounds__(128, MINB) k_bucket_acc(const Affine<F>* __res
     buckets[key] = acc;
 }
 
+#ifdef OG_MSM_G2
+// G2 variant with the 256-byte accumulator in shared memory (16-byte chunks interleaved over the CTA's threads, so
+// every access is conflict-free): registers hold only the temporaries of one mixed addition, which buys resident
+// warps in a kernel whose top stall is the fixed-latency wait of the carry chains (OG_ACC_OCC_G2 = 14, 15, 16).
+struct SmAcc {
+    uint4* base;    // [16 chunks][128 threads]
+    __device__ __forceinline__ Fq2 ld(int coord) const {
+        Fq2 v;
+        uint4 a = base[(coord * 4 + 0) * 128], b = base[(coord * 4 + 1) * 128], c = base[(coord * 4 + 2) * 128], d = base[(coord * 4 + 3) * 128];
+        v.c0.l[0] = a.x; v.c0.l[1] = a.y; v.c0.l[2] = a.z; v.c0.l[3] = a.w; v.c0.l[4] = b.x; v.c0.l[5] = b.y; v.c0.l[6] = b.z; v.c0.l[7] = b.w;
+        v.c1.l[0] = c.x; v.c1.l[1] = c.y; v.c1.l[2] = c.z; v.c1.l[3] = c.w; v.c1.l[4] = d.x; v.c1.l[5] = d.y; v.c1.l[6] = d.z; v.c1.l[7] = d.w;
+        return v;
+    }
+    __device__ __forceinline__ void st(int coord, const Fq2& v) const {
+        base[(coord * 4 + 0) * 128] = make_uint4(v.c0.l[0], v.c0.l[1], v.c0.l[2], v.c0.l[3]);
+        base[(coord * 4 + 1) * 128] = make_uint4(v.c0.l[4], v.c0.l[5], v.c0.l[6], v.c0.l[7]);
+        base[(coord * 4 + 2) * 128] = make_uint4(v.c1.l[0], v.c1.l[1], v.c1.l[2], v.c1.l[3]);
+        base[(coord * 4 + 3) * 128] = make_uint4(v.c1.l[4], v.c1.l[5], v.c1.l[6], v.c1.l[7]);
+    }
+};
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_bucket_acc_sm(const Affine<Fq2>* __restrict__ table, const uint32_t* __restrict__ sorted,
+                                                       const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                                       uint32_t n_keys, uint32_t cap, XYZZ<Fq2>* __restrict__ buckets,
+                                                       uint32_t* __restrict__ heavy, const uint32_t* __restrict__ perm) {
+    __shared__ uint4 sm_acc[16 * 128];
+    uint32_t slot_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot_ >= n_keys) return;
+    uint32_t key = perm[slot_];
+    uint32_t cnt = counts[key], off = offsets[key];
+    if (cnt > cap) {                               // left to k_bucket_heavy
+        uint32_t slot = atomicAdd(heavy, 1u);
+        heavy[1 + slot] = key;
+        buckets[key] = XYZZ<Fq2>::inf();
+        return;
+    }
+    SmAcc A{sm_acc + threadIdx.x};
+    bool inf = true;
+    uint32_t e = cnt ? sorted[off] : 0;
+    for (uint32_t k = 0; k < cnt; k++) {
+        uint32_t en = k + 1 < cnt ? sorted[off + k + 1] : 0;
+        Affine<Fq2> q = fetch_point(table, e);
+        e = en;
+        if (q.is_inf()) continue;
+        if (inf) { A.st(0, q.x); A.st(1, q.y); A.st(2, Fq2::one()); A.st(3, Fq2::one()); inf = false; continue; }
+        Fq2 p = q.x * A.ld(2) - A.ld(0);
+        Fq2 r = q.y * A.ld(3) - A.ld(1);
+        if (p.is_zero()) {
+            if (r.is_zero()) { XYZZ<Fq2> d = XYZZ<Fq2>::dbl_affine(q); A.st(0, d.x); A.st(1, d.y); A.st(2, d.zz); A.st(3, d.zzz); }
+            else inf = true;
+            continue;
+        }
+        Fq2 pp = p.sqr();
+        Fq2 ppp = p * pp;
+        Fq2 q1 = A.ld(0) * pp;
+        Fq2 x3 = r.sqr() - ppp - q1.dbl();
+        A.st(0, x3);
+        A.st(1, r * (q1 - x3) - A.ld(1) * ppp);
+        A.st(2, A.ld(2) * pp);
+        A.st(3, A.ld(3) * ppp);
+    }
+    buckets[key] = inf ? XYZZ<Fq2>::inf() : XYZZ<Fq2>{A.ld(0), A.ld(1), A.ld(2), A.ld(3)};
+}
+#endif
+
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_bucket_heavy(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
                                                           const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
@@ -513,6 +579,11 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
             else { auto k = k_bucket_acc<F, 5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
         } else {
             if (occ == 2) { auto k = k_bucket_acc<F, 2>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+#ifdef OG_MSM_G2
+            else if (occ == 14) { auto k = k_bucket_acc_sm<4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 15) { auto k = k_bucket_acc_sm<5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 16) { auto k = k_bucket_acc_sm<6>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+#endif
             else if (occ == 4) { auto k = k_bucket_acc<F, 4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
             else { auto k = k_bucket_acc<F, 3>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
         }
