@@ -424,6 +424,74 @@ __global__ void __launch_bounds__(128, MINB) k_bucket_acc(const Affine<F>* __res
     buckets[key] = acc;
 }
 
+#ifdef OG_MSM_G1
+// G1 variant with the 128-byte accumulator in shared memory (see the G2 one below): 8 chunks of 16 bytes per thread.
+struct SmAcc1 {
+    uint4* base;    // [8 chunks][128 threads]
+    __device__ __forceinline__ Fq ld(int coord) const {
+        Fq v;
+        uint4 a = base[(coord * 2 + 0) * 128], b = base[(coord * 2 + 1) * 128];
+        v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+        return v;
+    }
+    __device__ __forceinline__ void st(int coord, const Fq& v) const {
+        base[(coord * 2 + 0) * 128] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        base[(coord * 2 + 1) * 128] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+};
+
+template <int MINB, bool PREFETCH>
+__global__ void __launch_bounds__(128, MINB) k_bucket_acc_sm1(const Affine<Fq>* __restrict__ table, const uint32_t* __restrict__ sorted,
+                                                        const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                                        uint32_t n_keys, uint32_t cap, XYZZ<Fq>* __restrict__ buckets,
+                                                        uint32_t* __restrict__ heavy, const uint32_t* __restrict__ perm) {
+    __shared__ uint4 sm_acc[8 * 128];
+    uint32_t slot_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot_ >= n_keys) return;
+    uint32_t key = perm[slot_];
+    uint32_t cnt = counts[key], off = offsets[key];
+    if (cnt > cap) {                               // left to k_bucket_heavy
+        uint32_t slot = atomicAdd(heavy, 1u);
+        heavy[1 + slot] = key;
+        buckets[key] = XYZZ<Fq>::inf();
+        return;
+    }
+    SmAcc1 A{sm_acc + threadIdx.x};
+    bool inf = true;
+    Affine<Fq> nxt = (PREFETCH && cnt) ? fetch_point(table, sorted[off]) : Affine<Fq>::inf();
+    uint32_t e = (!PREFETCH && cnt) ? sorted[off] : 0;
+    for (uint32_t k = 0; k < cnt; k++) {
+        Affine<Fq> q;
+        if (PREFETCH) {
+            q = nxt;
+            if (k + 1 < cnt) nxt = fetch_point(table, sorted[off + k + 1]);   // overlap the gather with the add
+        } else {
+            uint32_t en = k + 1 < cnt ? sorted[off + k + 1] : 0;                // only the next entry is read ahead
+            q = fetch_point(table, e);
+            e = en;
+        }
+        if (q.is_inf()) continue;
+        if (inf) { A.st(0, q.x); A.st(1, q.y); A.st(2, Fq::one()); A.st(3, Fq::one()); inf = false; continue; }
+        Fq p = q.x * A.ld(2) - A.ld(0);
+        Fq r = q.y * A.ld(3) - A.ld(1);
+        if (p.is_zero()) {
+            if (r.is_zero()) { XYZZ<Fq> d = XYZZ<Fq>::dbl_affine(q); A.st(0, d.x); A.st(1, d.y); A.st(2, d.zz); A.st(3, d.zzz); }
+            else inf = true;
+            continue;
+        }
+        Fq pp = p.sqr();
+        Fq ppp = p * pp;
+        Fq q1 = A.ld(0) * pp;
+        Fq x3 = r.sqr() - ppp - q1.dbl();
+        A.st(0, x3);
+        A.st(1, r * (q1 - x3) - A.ld(1) * ppp);
+        A.st(2, A.ld(2) * pp);
+        A.st(3, A.ld(3) * ppp);
+    }
+    buckets[key] = inf ? XYZZ<Fq>::inf() : XYZZ<Fq>{A.ld(0), A.ld(1), A.ld(2), A.ld(3)};
+}
+#endif
+
 #ifdef OG_MSM_G2
 // G2 variant with the 256-byte accumulator in shared memory (16-byte chunks interleaved over the CTA's threads, so
 // every access is conflict-free): registers hold only the temporaries of one mixed addition, which buys resident
@@ -546,6 +614,83 @@ __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__
     U_out[(size_t)g * n_out + p] = T;
 }
 
+#ifdef OG_MSM_G1
+// G1 reduction level with both running sums in shared memory (same idea as k_bucket_acc_sm1): the plain kernel
+// needs 226 registers, i.e. 2 warps per scheduler; this one keeps only the temporaries of one addition.
+// acc += o, accumulator behind ld/st accessors, o in registers
+template <class ACC>
+__device__ __forceinline__ void add_into(const ACC& A, bool& a_inf, const XYZZ<Fq>& o) {
+    if (o.is_inf()) return;
+    if (a_inf) { A.st(0, o.x); A.st(1, o.y); A.st(2, o.zz); A.st(3, o.zzz); a_inf = false; return; }
+    Fq u1 = A.ld(0) * o.zz;
+    Fq p = o.x * A.ld(2) - u1;
+    Fq s1 = A.ld(1) * o.zzz;
+    Fq r = o.y * A.ld(3) - s1;
+    if (p.is_zero()) {
+        if (r.is_zero()) {
+            XYZZ<Fq> d = XYZZ<Fq>{A.ld(0), A.ld(1), A.ld(2), A.ld(3)}.dbl();
+            A.st(0, d.x); A.st(1, d.y); A.st(2, d.zz); A.st(3, d.zzz);
+        } else {
+            a_inf = true;
+        }
+        return;
+    }
+    Fq pp = p.sqr();
+    Fq ppp = p * pp;
+    Fq q1 = u1 * pp;
+    Fq x3 = r.sqr() - ppp - q1.dbl();
+    A.st(0, x3);
+    A.st(1, r * (q1 - x3) - s1 * ppp);
+    A.st(2, A.ld(2) * o.zz * pp);
+    A.st(3, A.ld(3) * o.zzz * ppp);
+}
+
+struct SmAccR {     // [8 chunks][64 threads]
+    uint4* base;
+    __device__ __forceinline__ Fq ld(int coord) const {
+        Fq v;
+        uint4 a = base[(coord * 2 + 0) * 64], b = base[(coord * 2 + 1) * 64];
+        v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+        return v;
+    }
+    __device__ __forceinline__ void st(int coord, const Fq& v) const {
+        base[(coord * 2 + 0) * 64] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        base[(coord * 2 + 1) * 64] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+    __device__ __forceinline__ XYZZ<Fq> get(bool inf) const { return inf ? XYZZ<Fq>::inf() : XYZZ<Fq>{ld(0), ld(1), ld(2), ld(3)}; }
+};
+
+template <bool HAS_U>
+__global__ void __launch_bounds__(64, 8) k_reduce_level_sm(const XYZZ<Fq>* __restrict__ S_in, const XYZZ<Fq>* __restrict__ U_in,
+                                                           uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
+                                                           uint32_t fan_log2, XYZZ<Fq>* __restrict__ S_out, XYZZ<Fq>* __restrict__ U_out) {
+    __shared__ uint4 sm_r[8 * 64], sm_t[8 * 64];
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups * n_out) return;
+    uint32_t g = t / n_out, p = t % n_out;
+    const XYZZ<Fq>* S = S_in + (size_t)g * n_in;
+    uint32_t lo = p << fan_log2, hi = min(n_in, lo + (1u << fan_log2));
+    SmAccR R{sm_r + threadIdx.x}, T{sm_t + threadIdx.x};
+    bool r_inf = true, t_inf = true;
+    for (uint32_t i = hi - 1; i > lo; i--) {
+        add_into(R, r_inf, S[i]);
+        add_into(T, t_inf, R.get(r_inf));
+    }
+    add_into(R, r_inf, S[lo]);
+    XYZZ<Fq> Tv = T.get(t_inf);
+    for (uint32_t k = 0; k < w_log2; k++) Tv = Tv.dbl();
+    if (HAS_U) {
+        const XYZZ<Fq>* U = U_in + (size_t)g * n_in;
+        T.st(0, Tv.x); T.st(1, Tv.y); T.st(2, Tv.zz); T.st(3, Tv.zzz);
+        t_inf = Tv.is_inf();
+        for (uint32_t i = lo; i < hi; i++) add_into(T, t_inf, U[i]);
+        Tv = T.get(t_inf);
+    }
+    S_out[(size_t)g * n_out + p] = R.get(r_inf);
+    U_out[(size_t)g * n_out + p] = Tv;
+}
+#endif
+
 // total_g = U_g + S_g   (weights are b+1)
 template <class F>
 __global__ void __launch_bounds__(64) k_group_total(const XYZZ<F>* __restrict__ S, const XYZZ<F>* __restrict__ U, uint32_t n_groups,
@@ -574,6 +719,15 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
         const char* kn = sizeof(F) == 32 ? "k_bucket_acc_g1" : "k_bucket_acc_g2";
         unsigned grid = (n_keys + 127) / 128;
         if constexpr (sizeof(F) == 32) {
+#ifdef OG_MSM_G1
+            if (occ == 17) { auto k = k_bucket_acc_sm1<7, true>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 18) { auto k = k_bucket_acc_sm1<8, true>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 26) { auto k = k_bucket_acc_sm1<6, false>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 27) { auto k = k_bucket_acc_sm1<7, false>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 0 || occ == 28) { auto k = k_bucket_acc_sm1<8, false>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 16) { auto k = k_bucket_acc_sm1<6, true>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else
+#endif
             if (occ == 4) { auto k = k_bucket_acc<F, 4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
             else if (occ == 6) { auto k = k_bucket_acc<F, 6>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
             else { auto k = k_bucket_acc<F, 5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
@@ -582,7 +736,7 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
 #ifdef OG_MSM_G2
             else if (occ == 14) { auto k = k_bucket_acc_sm<4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
             else if (occ == 15) { auto k = k_bucket_acc_sm<5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 16) { auto k = k_bucket_acc_sm<6>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
+            else if (occ == 0 || occ == 16) { auto k = k_bucket_acc_sm<6>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
 #endif
             else if (occ == 4) { auto k = k_bucket_acc<F, 4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
             else { auto k = k_bucket_acc<F, 3>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
@@ -606,6 +760,12 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
         uint32_t n_out = (n_in + (1u << fan_log2) - 1) >> fan_log2;
         uint32_t threads = n_groups * n_out;
         const char* rn = sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2";
+#ifdef OG_MSM_G1
+        static const int red_sm = [] { const char* v = getenv("OG_RED_SM"); return v ? atoi(v) : 0; }();
+        if (red_sm && U_in) { auto k = k_reduce_level_sm<true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+        else if (red_sm) { auto k = k_reduce_level_sm<false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+        else
+#endif
         if (U_in) { auto k = k_reduce_level<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
         else { auto k = k_reduce_level<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
         S_in = bufS[pp]; U_in = bufU[pp];
