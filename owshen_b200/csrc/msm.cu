@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restric
         if (!SCATTER) {
             atomicAdd(&counts[key], 1u);
         } else {
-            uint32_t pos = offsets[key] + atomicAdd(&cursor[key], 1u);
+            uint32_t pos = atomicAdd(&cursor[key], 1u);          // cursor starts at the bucket's offset (k_scan_apply)
             sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
         }
     });
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits_tiled(DigitPlan P, uint3
     } else {
     for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) {
         uint32_t h = hist[b];
-        base[b] = h ? offsets[key0 + b] + atomicAdd(&cursor[key0 + b], h) : 0;
+        base[b] = h ? atomicAdd(&cursor[key0 + b], h) : 0;
         hist[b] = 0;                                                  // reused as the running rank inside the run
     }
     __syncthreads();
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(uint32_t* __res
     if (threadIdx.x == 0) *grand_total = run;
 }
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ counts, uint32_t n, const uint32_t* __restrict__ tile_sums,
-                                                            uint32_t* __restrict__ offsets) {
+                                                            uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
     uint32_t c[SCAN_PER_THREAD], s = 0;
 #pragma unroll
@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
     uint32_t total;
     uint32_t run = tile_sums[blockIdx.x] + block_exclusive_scan(s, &total);
 #pragma unroll
-    for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) { if (base + k < n) offsets[base + k] = run; run += c[k]; }
+    for (uint32_t k = 0; k < SCAN_PER_THREAD; k++) {      // the scatter's cursors start at the offsets: one random access per entry fewer
+        if (base + k < n) { offsets[base + k] = run; cursor[base + k] = run; }
+        run += c[k];
+    }
 }
 
 int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uint32_t* d_counts, uint32_t* d_offsets,
@@ -309,7 +312,6 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
         return OG_OK;
     }
     OG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)n_keys, ctx->stream));
-    OG_CUDA(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(uint32_t) * (size_t)n_keys, ctx->stream));
     if (plan.n == 0 || plan.n_problems == 0) {
         OG_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * ((size_t)n_keys + 1), ctx->stream));
         return OG_OK;
@@ -323,12 +325,12 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
     dim3 tgrid((unsigned)((plan.n + DIG_TILE - 1) / DIG_TILE), plan.n_problems);
     if (tiled) OG_LAUNCHN(ctx, "k_digits_tiled<count>", k_digits_tiled<false>, tgrid, DIG_THREADS, 4 * (size_t)plan.nb, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
     else OG_LAUNCH(ctx, k_digits<false>, grid, 256, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
-    {   // offsets[n_keys] receives the grand total; the tile sums live in the cursor array (zeroed again below)
+    {   // offsets[n_keys] receives the grand total; cursor[k] = offsets[k] for the scatter
         uint32_t n_tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
         OG_SLOT(ctx, tile_sums, uint32_t, S_MSM_MISC, 4 * (size_t)n_tiles);
         OG_LAUNCH(ctx, k_scan_tiles, n_tiles, SCAN_THREADS, 0, d_counts, n_keys, tile_sums);
         OG_LAUNCH(ctx, k_scan_tile_sums, 1, SCAN_THREADS, 0, tile_sums, n_tiles, d_offsets + n_keys);
-        OG_LAUNCH(ctx, k_scan_apply, n_tiles, SCAN_THREADS, 0, d_counts, n_keys, tile_sums, d_offsets);
+        OG_LAUNCH(ctx, k_scan_apply, n_tiles, SCAN_THREADS, 0, d_counts, n_keys, tile_sums, d_offsets, d_cursor);
     }
     // measured: the tiled scatter (run reservation + shared-memory ranks) is slower than the plain one
     // (39 vs 33 ms per 1024 proofs) while the tiled count is 5x faster (5 vs 24 ms) -> tiled count, plain scatter
@@ -587,7 +589,9 @@ constexpr uint32_t RED_FAN_LOG2 = 3, RED_FAN = 1u << RED_FAN_LOG2;   // 8 childr
 // relative to e's first bucket).  Merging children c_0..c_k, each covering 2^w_log2 buckets:
 //   S_p = sum S_c;   U_p = sum U_c + 2^w_log2 * sum_c idx(c) * S_c   (running-sum trick for the last term).
 // HAS_U = false is level 0 (children are raw buckets, no weighted part yet): most of the work, and one 4-coordinate
-// accumulator fewer to keep in registers.
+// accumulator fewer to keep in registers.  (A variant with R and T in shared memory -- 128 instead of 226 registers,
+// twice the resident warps -- was measured slower, 32.7 vs 30.7 ms per step for G1: the R -> T chain, not occupancy,
+// is what this kernel waits on.)
 template <class F, bool HAS_U>
 __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
                                                      uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
@@ -613,83 +617,6 @@ __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__
     S_out[(size_t)g * n_out + p] = R;
     U_out[(size_t)g * n_out + p] = T;
 }
-
-#ifdef OG_MSM_G1
-// G1 reduction level with both running sums in shared memory (same idea as k_bucket_acc_sm1): the plain kernel
-// needs 226 registers, i.e. 2 warps per scheduler; this one keeps only the temporaries of one addition.
-// acc += o, accumulator behind ld/st accessors, o in registers
-template <class ACC>
-__device__ __forceinline__ void add_into(const ACC& A, bool& a_inf, const XYZZ<Fq>& o) {
-    if (o.is_inf()) return;
-    if (a_inf) { A.st(0, o.x); A.st(1, o.y); A.st(2, o.zz); A.st(3, o.zzz); a_inf = false; return; }
-    Fq u1 = A.ld(0) * o.zz;
-    Fq p = o.x * A.ld(2) - u1;
-    Fq s1 = A.ld(1) * o.zzz;
-    Fq r = o.y * A.ld(3) - s1;
-    if (p.is_zero()) {
-        if (r.is_zero()) {
-            XYZZ<Fq> d = XYZZ<Fq>{A.ld(0), A.ld(1), A.ld(2), A.ld(3)}.dbl();
-            A.st(0, d.x); A.st(1, d.y); A.st(2, d.zz); A.st(3, d.zzz);
-        } else {
-            a_inf = true;
-        }
-        return;
-    }
-    Fq pp = p.sqr();
-    Fq ppp = p * pp;
-    Fq q1 = u1 * pp;
-    Fq x3 = r.sqr() - ppp - q1.dbl();
-    A.st(0, x3);
-    A.st(1, r * (q1 - x3) - s1 * ppp);
-    A.st(2, A.ld(2) * o.zz * pp);
-    A.st(3, A.ld(3) * o.zzz * ppp);
-}
-
-struct SmAccR {     // [8 chunks][64 threads]
-    uint4* base;
-    __device__ __forceinline__ Fq ld(int coord) const {
-        Fq v;
-        uint4 a = base[(coord * 2 + 0) * 64], b = base[(coord * 2 + 1) * 64];
-        v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
-        return v;
-    }
-    __device__ __forceinline__ void st(int coord, const Fq& v) const {
-        base[(coord * 2 + 0) * 64] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-        base[(coord * 2 + 1) * 64] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-    }
-    __device__ __forceinline__ XYZZ<Fq> get(bool inf) const { return inf ? XYZZ<Fq>::inf() : XYZZ<Fq>{ld(0), ld(1), ld(2), ld(3)}; }
-};
-
-template <bool HAS_U>
-__global__ void __launch_bounds__(64, 8) k_reduce_level_sm(const XYZZ<Fq>* __restrict__ S_in, const XYZZ<Fq>* __restrict__ U_in,
-                                                           uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
-                                                           uint32_t fan_log2, XYZZ<Fq>* __restrict__ S_out, XYZZ<Fq>* __restrict__ U_out) {
-    __shared__ uint4 sm_r[8 * 64], sm_t[8 * 64];
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_groups * n_out) return;
-    uint32_t g = t / n_out, p = t % n_out;
-    const XYZZ<Fq>* S = S_in + (size_t)g * n_in;
-    uint32_t lo = p << fan_log2, hi = min(n_in, lo + (1u << fan_log2));
-    SmAccR R{sm_r + threadIdx.x}, T{sm_t + threadIdx.x};
-    bool r_inf = true, t_inf = true;
-    for (uint32_t i = hi - 1; i > lo; i--) {
-        add_into(R, r_inf, S[i]);
-        add_into(T, t_inf, R.get(r_inf));
-    }
-    add_into(R, r_inf, S[lo]);
-    XYZZ<Fq> Tv = T.get(t_inf);
-    for (uint32_t k = 0; k < w_log2; k++) Tv = Tv.dbl();
-    if (HAS_U) {
-        const XYZZ<Fq>* U = U_in + (size_t)g * n_in;
-        T.st(0, Tv.x); T.st(1, Tv.y); T.st(2, Tv.zz); T.st(3, Tv.zzz);
-        t_inf = Tv.is_inf();
-        for (uint32_t i = lo; i < hi; i++) add_into(T, t_inf, U[i]);
-        Tv = T.get(t_inf);
-    }
-    S_out[(size_t)g * n_out + p] = R.get(r_inf);
-    U_out[(size_t)g * n_out + p] = Tv;
-}
-#endif
 
 // total_g = U_g + S_g   (weights are b+1)
 template <class F>
@@ -760,12 +687,6 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
         uint32_t n_out = (n_in + (1u << fan_log2) - 1) >> fan_log2;
         uint32_t threads = n_groups * n_out;
         const char* rn = sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2";
-#ifdef OG_MSM_G1
-        static const int red_sm = [] { const char* v = getenv("OG_RED_SM"); return v ? atoi(v) : 0; }();
-        if (red_sm && U_in) { auto k = k_reduce_level_sm<true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
-        else if (red_sm) { auto k = k_reduce_level_sm<false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
-        else
-#endif
         if (U_in) { auto k = k_reduce_level<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
         else { auto k = k_reduce_level<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
         S_in = bufS[pp]; U_in = bufU[pp];
