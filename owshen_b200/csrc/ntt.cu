@@ -127,7 +127,10 @@ __device__ __forceinline__ void sm_put(uint4* sm, uint32_t e, const Fr& v) {
     sm[sw_chunk(e, 1)] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-__global__ void __launch_bounds__(256) k_ntt_pass2(PassPlan P, const Fr* __restrict__ in, Fr* __restrict__ out,
+// MINB = resident CTAs per SM requested from ptxas for the 256-thread launches (registers <-> warps that can cover
+// the barriers and the gather/scatter phases of their neighbours); measured, see OG_NTT_OCC
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ntt_pass2(PassPlan P, const Fr* __restrict__ in, Fr* __restrict__ out,
                                                    const Fr* __restrict__ t2, Fr n_inv) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     uint4* sm = reinterpret_cast<uint4*>(smem_raw);
@@ -287,7 +290,11 @@ int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t ba
             uint32_t threads = tile / 4 < 32 ? 32 : (tile / 4 > 256 ? 256 : tile / 4);
             // the swizzle permutes chunks inside groups of 8 elements: pad tiny tiles up to one group
             size_t smem = (tile < 8 ? 8 : tile) * sizeof(Fr);
-            OG_LAUNCHN(ctx, "k_ntt_pass", k_ntt_pass2, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv);
+            static const int occ = [] { const char* e = getenv("OG_NTT_OCC"); return e ? atoi(e) : 0; }();
+            if (occ == 0 || occ == 3) { auto k = k_ntt_pass2<3>; OG_LAUNCHN(ctx, "k_ntt_pass", k, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv); }
+            else if (occ == 4) { auto k = k_ntt_pass2<4>; OG_LAUNCHN(ctx, "k_ntt_pass", k, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv); }
+            else if (occ == 2) { auto k = k_ntt_pass2<2>; OG_LAUNCHN(ctx, "k_ntt_pass", k, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv); }
+            else { auto k = k_ntt_pass2<1>; OG_LAUNCHN(ctx, "k_ntt_pass", k, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv); }
         }
     }
     return OG_OK;
