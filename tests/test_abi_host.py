@@ -29,6 +29,42 @@ def test_every_declared_symbol_is_exported():
     assert L.og_abi_version() == 1
 
 
+def test_header_prototypes_match_the_ctypes_mirror():
+    """Parameter counts (and pointer-ness of every parameter) of include/owshen_b200.h against api.ABI_SYMBOLS:
+    a drifted mirror would pass garbage across the boundary without any loader error."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, "include", "owshen_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    protos = dict(re.findall(r"\b(og_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr))
+    assert set(protos) == set(api.ABI_SYMBOLS)
+    for name, params in protos.items():
+        params = params.strip()
+        plist = [] if params in ("", "void") else [x.strip() for x in params.split(",")]
+        res, args = api._SIGS[name]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, api.py {len(args)}"
+        for decl, ct in zip(plist, args):
+            is_ptr_c = "*" in decl
+            is_ptr_py = ct in (C.c_void_p, C.c_char_p) or isinstance(ct, type) and issubclass(ct, C._Pointer)
+            assert is_ptr_c == is_ptr_py, f"{name}: `{decl}` vs {ct}"
+            if not is_ptr_c:
+                width = 8 if "64" in decl else 4
+                assert C.sizeof(ct) == width, f"{name}: `{decl}` vs {ct}"
+
+
+def test_rust_bindings_are_in_step_with_the_header():
+    """bindings/rust/ffi.rs is generated from include/owshen_b200.h (scripts/gen_rust_ffi.py); it cannot be compiled
+    here (no rustc), so at least it must not drift."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_rust_ffi.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ffi = open(os.path.join(ROOT, "bindings", "rust", "ffi.rs")).read()
+    assert ffi.count("pub fn og_") == len(api.ABI_SYMBOLS)
+    wrapper = open(os.path.join(ROOT, "bindings", "rust", "prover.rs")).read()
+    for used in set(re.findall(r"ffi::(og_[a-z0-9_]+)", wrapper)):
+        assert f"pub fn {used}(" in ffi, used
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
