@@ -446,9 +446,17 @@ class MerkleTree:
         return self._get(self.depth, 0)
 
     def path(self, idx: int):
+        if not 0 <= idx < self.n_leaves:
+            raise IndexError(f"leaf {idx} not in the tree ({self.n_leaves} leaves)")
         sibs, bits, i = [], 0, idx
         for lvl in range(self.depth):
             sibs.append(self._get(lvl, i ^ 1))
             bits |= (i & 1) << lvl
             i >>= 1
         return b"".join(sibs), bits
+
+    def paths(self, indices):
+        """Authentication paths of many leaves in the layout prove() takes: (siblings, path_bits) with siblings =
+        len(indices) x depth x 32 bytes, proof-major, and one path_bits word per leaf."""
+        got = [self.path(i) for i in indices]
+        return b"".join(s for s, _ in got), [b for _, b in got]
