@@ -133,6 +133,45 @@ def physical_cores():
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
+def host_cpu_info():
+    """What the CPU arm can actually use on this box, so that ratios compare across boxes: affinity mask, cgroup
+    quota, SMT layout, load before the run (round 1 saw 8.6 vs 34 proofs/s on two boxes that both said "64 cores")."""
+    info = {"affinity": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None, "os_cpu_count": os.cpu_count()}
+    try:
+        import psutil
+        info["physical"] = psutil.cpu_count(logical=False)
+        info["logical"] = psutil.cpu_count(logical=True)
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        info["cgroup_cpu_max"] = None if q == "max" else float(q) / float(per)
+    except Exception:
+        info["cgroup_cpu_max"] = "unreadable"
+    try:
+        info["loadavg_1m"] = os.getloadavg()[0]
+    except Exception:
+        pass
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                info["model"] = line.split(":", 1)[1].strip(); break
+    except Exception:
+        pass
+    return info
+
+
+def cpu_single_thread_seconds(pr, rng):
+    """Seconds for ONE proof on ONE host thread (box-independent yardstick next to the all-cores rate)."""
+    from oracle import cport
+    cport.lib().oc_set_num_threads(1)
+    nul, sec, rec, sib, bits, rs = synth_inputs(rng, 1, DEPTH)
+    wit = cport.withdraw_witness(nul, sec, rec, sib, bits, DEPTH)
+    t = time.perf_counter()
+    pr.prove_batch(wit, rs)
+    return time.perf_counter() - t
+
+
 def cpu_prover_rate(pkb, n_proofs, rng, threads=None):
     """proofs/s of the oracle's C prover on `n_proofs` synthetic witnesses, one proof per host thread."""
     from oracle import cport
@@ -147,7 +186,99 @@ def cpu_prover_rate(pkb, n_proofs, rng, threads=None):
     t = time.perf_counter()
     pr.prove_batch(wit, rs)
     dt = time.perf_counter() - t
-    return n_proofs / dt, cores, dt
+    one = cpu_single_thread_seconds(pr, random.Random(11))
+    return n_proofs / dt, cores, dt, one
+
+
+def synth_scalars_dev(torch, seed, lo, hi, dev):
+    """Scalars [lo, hi) of a seeded 253-bit sequence as a device uint8 tensor (32 B each, always canonical);
+    reproducible per block of 2^16, so any rank can regenerate any range."""
+    blk, parts = 1 << 16, []
+    for b0 in range(lo - lo % blk, hi, blk):
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed * 1000003 + b0 // blk)
+        raw = torch.randint(0, 256, (blk, 32), dtype=torch.uint8, device=dev, generator=g)
+        raw[:, 31] &= 0x1F
+        a, b = max(lo, b0) - b0, min(hi, b0 + blk) - b0
+        parts.append(raw[a:b].reshape(-1))
+    return torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device=dev)
+
+
+def sharded_msm_leg(torch, dist, ob, api, ctx, dev, rank, world, log_n, steps=3, warmup=1):
+    """BASELINE config 5 through the product function owshen_b200.sharded.msm_sharded_dev: one G1 + one G2 MSM of
+    2^log_n points (shared scalars) sharded by point range over the ranks, partial sums all-gathered over NCCL on
+    the library's stream, CUDA-event timed on that stream, max over ranks.  Rank 0 then recomputes the whole MSM on
+    its GPU alone: `matches_single_gpu` and the strong-scaling ratio come from that."""
+    from owshen_b200.sharded import msm_sharded_dev, shard_range
+    L = api.lib()
+    n = 1 << log_n
+
+    def inputs(lo, hi):
+        m = hi - lo
+        ks = synth_scalars_dev(torch, 5, lo, hi, dev)
+        sc = synth_scalars_dev(torch, 55, lo, hi, dev)
+        p1 = torch.empty(64 * m, dtype=torch.uint8, device=dev)
+        p2 = torch.empty(128 * m, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        api._check(L.og_g1_generator_mul_dev(ctx._h, ks.data_ptr(), m, p1.data_ptr()), ctx)
+        api._check(L.og_g2_generator_mul_dev(ctx._h, ks.data_ptr(), m, p2.data_ptr()), ctx)
+        ctx.sync()
+        return p1, p2, sc
+
+    lo, hi = shard_range(n, rank, world)
+    p1, p2, sc = inputs(lo, hi)
+    out1 = torch.empty(64, dtype=torch.uint8, device=dev)
+    out2 = torch.empty(128, dtype=torch.uint8, device=dev)
+
+    def one():
+        msm_sharded_dev(ctx, p1, sc, "g1", out=out1)
+        msm_sharded_dev(ctx, p2, sc, "g2", out=out2)
+    for _ in range(warmup):
+        one()
+    ctx.sync(); torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    ctx.timer_start()
+    for _ in range(steps):
+        one()
+    ms = ctx.timer_stop() / steps
+    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+    mine = torch.cat([out1, out2]).clone()
+    agree = torch.ones(1, dtype=torch.int32, device=dev)
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ref = mine.clone(); dist.broadcast(ref, 0)
+        agree = torch.tensor([int(torch.equal(mine, ref))], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+    ms = float(tt.item())
+    single_ms, matches = None, None
+    if rank == 0:
+        if world > 1:
+            del p1, p2, sc
+            p1, p2, sc = inputs(0, n)
+        s1 = torch.empty(64, dtype=torch.uint8, device=dev)
+        s2 = torch.empty(128, dtype=torch.uint8, device=dev)
+
+        def alone():
+            api._check(L.og_msm_g1_dev(ctx._h, p1.data_ptr(), sc.data_ptr(), n, s1.data_ptr()), ctx)
+            api._check(L.og_msm_g2_dev(ctx._h, p2.data_ptr(), sc.data_ptr(), n, s2.data_ptr()), ctx)
+        alone(); ctx.sync()
+        ctx.timer_start()
+        for _ in range(steps):
+            alone()
+        single_ms = ctx.timer_stop() / steps
+        matches = bool(torch.equal(torch.cat([s1, s2]), mine))
+    if dist:
+        dist.barrier()
+    alg = (64 + 128 + 32) * n
+    return {"workload": f"2^{log_n}-point G1 + G2 MSM, shared scalars, point-range sharded over {world} rank(s) (BASELINE config 5 shape; "
+                        f"2^24 needs the 8-GPU box, see scripts/bench_sharded_msm.py)",
+            "log_n": log_n, "n_gpus": world, "ms": ms, "points_per_s": n / (ms * 1e-3), "algorithmic_bytes": alg,
+            "hbm_gbs_aggregate": alg / (ms * 1e-3) / 1e9, "exchange_bytes_per_rank": 192, "ranks_agree": bool(agree.item()),
+            "matches_single_gpu": matches, "single_gpu_ms": single_ms,
+            "strong_scaling_vs_n1": (single_ms / ms) if single_ms else None,
+            "timing": "CUDA events on the library stream around MSM + NCCL all-gather (on that stream, no host hop) + final sum; max over ranks",
+            "steps": steps, "warmup": warmup}
 
 
 def run_reference(args):
@@ -167,6 +298,7 @@ def run_reference(args):
     nul, sec, rec, sib, bits, rs = synth_inputs(random.Random(1), sample, DEPTH)
     wit = cport.withdraw_witness(nul, sec, rec, sib, bits, DEPTH)
     pr = cport.Prover(cs, pkb)
+    host = host_cpu_info()
     for _ in range(args.warmup):
         pr.prove_batch(wit, rs)
     t = time.perf_counter()
@@ -174,14 +306,18 @@ def run_reference(args):
         pr.prove_batch(wit, rs)
     dt = time.perf_counter() - t
     value = sample * args.steps / dt
+    one = cpu_single_thread_seconds(pr, random.Random(11))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (4x64-bit Montgomery limbs)", "data": "synthetic",
         "config": {"workload": f"groth16 withdraw prove, depth-{DEPTH} MiMC7 Merkle, {sample} proofs per step on the CPU "
-                               f"(bounded sample of the {BATCH}-proof batch)", "circuit_constraints": cs.n_constraints},
+                               f"(bounded sample of the {BATCH}-proof batch: the full batch would take ~{BATCH * one / max(cores, 1):.0f} s "
+                               f"per step on this host, x {args.steps + args.warmup} steps; proofs are independent, so the rate does not depend on the batch)",
+                   "circuit_constraints": cs.n_constraints},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} proofs per step, one proof per OpenMP thread; own CPU prover -- the reference ships none"},
+                         "sample": f"{sample} proofs per step, one proof per OpenMP thread; own CPU prover -- the reference ships none",
+                         "single_thread_s_per_proof": one, "parallel_efficiency": value * one / max(cores, 1), "host": host},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -197,6 +333,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-parity", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--sharded-log-n", type=int, default=22, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -264,10 +402,13 @@ def main():
     launches = ctx.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
 
-    # parity spot-check of what was timed: proof 0 verifies against its own public inputs
+    # parity of what was timed: 16 proofs spread over the batch verify against their own public inputs (host pairing);
+    # below (rank 0), four of them are compared byte for byte with the oracle's C prover
     proofs_host = bytes(d_proofs.cpu().numpy().tobytes())
     pub_host = bytes(d_pub.cpu().numpy().tobytes())
-    verified = ob.verify(vk_bytes, pub_host[:96], proofs_host[:256])
+    vidx = sorted({(i * batch) // 16 for i in range(16)} | {batch - 1})
+    n_verified = sum(bool(ob.verify(vk_bytes, pub_host[96 * i:96 * i + 96], proofs_host[256 * i:256 * i + 256])) for i in vidx)
+    verified = n_verified == len(vidx)
 
     # e2e: host buffers (pinned) through the public host-pointer call
     def pinned(b):
@@ -294,6 +435,13 @@ def main():
     e2e_match = bytes(h_proofs.numpy().tobytes()) == proofs_host
     h2d = len(nul) + len(sec) + len(rec) + len(sib) + 4 * batch + len(rs)
     d2h = 256 * batch + 96 * batch
+
+    sharded = None
+    if args.sharded_log_n > 0:
+        try:
+            sharded = sharded_msm_leg(torch, dist, ob, api, ctx, dev, rank, world, args.sharded_log_n)
+        except Exception as e:      # an extra leg: its failure must not hide the headline
+            sharded = {"error": f"{type(e).__name__}: {e}"}
 
     # max over ranks
     times = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -332,6 +480,23 @@ def main():
         # 10 field multiplications per G1 mixed add, 128 32x32->64 multiply-adds per multiplication
         wide_mads = madds_per_proof_g1 * batch * args.steps * 10 * 128
         wide_rate = wide_mads / (kms * 1e-3) if kms > 0 else 0.0
+        parity = None
+        if not args.no_parity:
+            try:      # the oracle is the checker here, never the thing measured
+                from oracle import cport
+                from oracle import withdraw_circuit as wc
+                prng = random.Random(99)
+                pidx = [0, batch - 1] + (sorted(prng.sample(range(1, batch - 1), 2)) if batch > 3 else [])
+                sel = lambda b, w: b"".join(b[w * i:w * i + w] for i in pidx)
+                cs = wc.build_r1cs(DEPTH)
+                pkb = parse_pk_blob(pk_bytes, info["n_vars"], info["n_pub"], info["log_m"])
+                wit = cport.withdraw_witness(sel(nul, 32), sel(sec, 32), sel(rec, 32), sel(sib, 32 * DEPTH), [bits[i] for i in pidx], DEPTH)
+                cport.lib().oc_set_num_threads(min(len(pidx), physical_cores()))
+                exp = cport.Prover(cs, pkb).prove_batch(wit, sel(rs, 64))
+                equal = [proofs_host[256 * i:256 * i + 256] == exp[256 * k:256 * k + 256] for k, i in enumerate(pidx)]
+                parity = {"proofs_compared_with_oracle": pidx, "bit_exact": all(equal), "verified": f"{n_verified}/{len(vidx)}"}
+            except Exception as e:
+                parity = {"error": str(e)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
             try:
@@ -340,9 +505,11 @@ def main():
                 cport.lib().oc_set_num_threads(physical_cores())
                 cores = cport.lib().oc_num_threads()
                 n_cpu = max(2 * cores, 16) if cores <= 64 else cores
-                rate, cores, dt = cpu_prover_rate(pkb, n_cpu, random.Random(7))
+                host = host_cpu_info()
+                rate, cores, dt, one = cpu_prover_rate(pkb, n_cpu, random.Random(7))
                 cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                       "sample": f"{n_cpu} proofs of the same workload, one per OpenMP thread, {dt:.1f} s wall; own CPU prover (oracle/cpu) -- the reference ships none"}
+                       "sample": f"{n_cpu} proofs of the same workload, one per OpenMP thread, {dt:.1f} s wall; own CPU prover (oracle/cpu) -- the reference ships none",
+                       "single_thread_s_per_proof": one, "parallel_efficiency": rate * one / max(cores, 1), "host": host}
             except Exception as e:  # the oracle is a checker; its absence must not hide the GPU number
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"unavailable: {e}"}
         value = world * batch * args.steps / (dev_ms * 1e-3)
@@ -355,7 +522,7 @@ def main():
                        "parallelism": f"replicas x{world} (independent proofs, no data-path collective)",
                        "l2": "per-step working set (sorted digit lists + window tables, > 2 GB) exceeds the 126 MB L2; no flush needed",
                        "timing": "CUDA events on the library stream, max over ranks", "wall_ms_per_step": wall_ms / args.steps,
-                       "proof0_verifies": bool(verified), "e2e_bytes_equal_device_path": bool(e2e_match)},
+                       "proofs_verify": bool(verified), "e2e_bytes_equal_device_path": bool(e2e_match), "parity": parity},
             "e2e": {"value": world * batch * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -371,6 +538,7 @@ def main():
                              "by og_int_pipe_peaks on this GPU in this run; achieved = mixed adds x 10 field muls x 128 products"},
             "kernels": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in top[:12]},
             "cpu_baseline": cpu,
+            "sharded_msm": sharded,
         }
         print(json.dumps(line))
     PK.close()

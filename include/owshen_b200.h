@@ -54,6 +54,10 @@ const char* og_last_error(const og_ctx* ctx);
 int32_t og_init(int32_t device, og_ctx** out);
 void og_free(og_ctx* ctx);
 int32_t og_sync(og_ctx* ctx);
+/* the CUDA stream (cudaStream_t) every `_dev` entry point of ctx enqueues on: a host that orders other work against
+ * the library without a host synchronisation (the NCCL all-gather of the sharded MSM) wraps it, e.g.
+ * torch.cuda.ExternalStream(ptr) */
+int32_t og_stream(og_ctx* ctx, void** out_cuda_stream);
 /* CUDA-event timer on the ctx stream (bench.py times kernels with these, not torch events) */
 int32_t og_timer_start(og_ctx* ctx);
 int32_t og_timer_stop(og_ctx* ctx, float* ms);
@@ -99,6 +103,12 @@ int32_t og_mimc7_merkle_paths_dev(og_ctx* ctx, const uint8_t* d_leaves, const ui
 /* full tree build: levels[0] = leaves (n = 2^depth_built padded by the caller), returns all
  * levels concatenated: sum_{l=0..log2 n} (n >> l) * 32 B */
 int32_t og_mimc7_merkle_build(og_ctx* ctx, const uint8_t* leaves, uint64_t n_leaves_pow2, uint8_t* out_levels);
+/* append to a fixed-depth sparse tree (the incremental builder of SURVEY.md 8f.2): all nodes of levels 1..depth
+ * touched by inserting n leaves at index `start`, in ONE call.  left_boundary[l] (32 B per level, l < depth) is the
+ * stored node (l, (start >> l) - 1) when (start >> l) is odd (ignored otherwise); zeros[l] is the root of an empty
+ * subtree of height l.  out_nodes: level 1 first, level l holds ((start+n-1)>>l) - (start>>l) + 1 nodes. */
+int32_t og_mimc7_merkle_append(og_ctx* ctx, uint32_t depth, uint64_t start, const uint8_t* leaves, uint64_t n,
+                               const uint8_t* left_boundary, const uint8_t* zeros, uint8_t* out_nodes);
 
 /* ---- BabyJubJub EdDSA-style batch verification -------------------------------------------
  * Replaces a loop over PointCompressed::verify, /root/reference/src/blockchain/tx/owshen_airdrop/babyjubjub/
@@ -117,9 +127,13 @@ int32_t og_msm_g2_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sca
 /* out_points[i] = scalars[i] * G for the standard generators (fixed-base windows on the GPU) */
 int32_t og_g1_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uint8_t* out_points64);
 int32_t og_g2_generator_mul(og_ctx* ctx, const uint8_t* scalars, uint64_t n, uint8_t* out_points128);
+int32_t og_g1_generator_mul_dev(og_ctx* ctx, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out_points64);
+int32_t og_g2_generator_mul_dev(og_ctx* ctx, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out_points128);
 /* plain sums of affine points: the local step after the multi-GPU all-gather of partial MSMs */
 int32_t og_g1_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out64);
 int32_t og_g2_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out128);
+int32_t og_g1_sum_dev(og_ctx* ctx, const uint8_t* d_points, uint64_t n, uint8_t* d_out64);
+int32_t og_g2_sum_dev(og_ctx* ctx, const uint8_t* d_points, uint64_t n, uint8_t* d_out128);
 
 /* ---- NTT over Fr -------------------------------------------------------------------------------- */
 /* `batch` independent transforms of 2^log_n elements, contiguous, natural order in and out.

@@ -5,9 +5,9 @@ everything below is a thin ctypes veneer over the C ABI in include/owshen_b200.h
 drop-in boundary (INTEGRATION.md shows the Rust binding).  There is no CPU fallback: importing works
 anywhere, but creating a Context without a CUDA device raises.
 """
-from .kvstore import KvStore, RamKvStore
+from .kvstore import KvStore, MirrorKvStore, RamKvStore
 from .api import (Context, ProvingKey, MerkleTree, OwshenB200Error, lib, build_library, prove, verify,
                   setup_withdraw, FR_MODULUS, PROOF_BYTES)
 
 __all__ = ["Context", "ProvingKey", "MerkleTree", "OwshenB200Error", "lib", "build_library", "prove", "verify",
-           "setup_withdraw", "FR_MODULUS", "PROOF_BYTES", "KvStore", "RamKvStore"]
+           "setup_withdraw", "FR_MODULUS", "PROOF_BYTES", "KvStore", "RamKvStore", "MirrorKvStore"]

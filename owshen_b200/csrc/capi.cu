@@ -14,7 +14,7 @@ using namespace og;
 void* og_ctx::slot(int id, size_t bytes) {
     if (bytes == 0) bytes = 32;
     if (slot_cap[id] >= bytes) return slot_ptr[id];
-    cudaStreamSynchronize(stream);
+    cudaDeviceSynchronize();          // growth is rare; other lanes may still be using neighbouring slots' kernels
     if (slot_ptr[id]) cudaFree(slot_ptr[id]);
     slot_ptr[id] = nullptr; slot_cap[id] = 0;
     size_t cap = bytes + bytes / 8;
@@ -106,6 +106,18 @@ int32_t og_init(int32_t device, og_ctx** out) {
         return OG_E_CUDA;
     }
     cudaMemset(ctx->d_flag, 0, sizeof(int));
+    ctx->main_stream = ctx->stream;
+    {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        bool ok = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&ctx->acc_ev, cudaEventDisableTiming) == cudaSuccess;
+        for (int l = 0; ok && l < MAX_LANES; l++)
+            ok = cudaStreamCreateWithPriority(&ctx->lane_hi[l], cudaStreamNonBlocking, greatest) == cudaSuccess &&
+                 cudaStreamCreateWithPriority(&ctx->lane_lo[l], cudaStreamNonBlocking, least) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->lane_ev[l], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) { og_free(ctx); return OG_E_CUDA; }
+    }
     int32_t rc = mimc_init(ctx);
     if (rc != OG_OK) { og_free(ctx); return rc; }
     *out = ctx;
@@ -115,7 +127,15 @@ int32_t og_init(int32_t device, og_ctx** out) {
 void og_free(og_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
+    ctx->stream = ctx->main_stream ? ctx->main_stream : ctx->stream;
+    for (int l = 0; l < MAX_LANES; l++) {
+        if (ctx->lane_hi[l]) cudaStreamDestroy(ctx->lane_hi[l]);
+        if (ctx->lane_lo[l]) cudaStreamDestroy(ctx->lane_lo[l]);
+        if (ctx->lane_ev[l]) cudaEventDestroy(ctx->lane_ev[l]);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->acc_ev) cudaEventDestroy(ctx->acc_ev);
     for (int i = 0; i < N_SLOTS; i++) if (ctx->slot_ptr[i]) cudaFree(ctx->slot_ptr[i]);
     ntt_free_tables(ctx);
     if (ctx->g1_fixed) cudaFree(ctx->g1_fixed);
@@ -134,6 +154,11 @@ int32_t og_sync(og_ctx* ctx) {
     OG_ENTER(ctx);
     if (!ctx) return OG_E_INVALID;
     OG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return OG_OK;
+}
+int32_t og_stream(og_ctx* ctx, void** out_cuda_stream) {
+    if (!ctx || !out_cuda_stream) return OG_E_INVALID;
+    *out_cuda_stream = (void*)ctx->main_stream;
     return OG_OK;
 }
 int32_t og_timer_start(og_ctx* ctx) {
@@ -535,6 +560,30 @@ int32_t og_mimc7_merkle_build(og_ctx* ctx, const uint8_t* leaves, uint64_t n, ui
     return check_flag(ctx);
 }
 
+// nodes of levels 1..depth touched by appending n leaves at index `start` to a depth-`depth` sparse tree: one call, no
+// host round trip per level.  Level l contributes ((start+n-1)>>l) - (start>>l) + 1 nodes, lowest index first.
+int32_t og_mimc7_merkle_append(og_ctx* ctx, uint32_t depth, uint64_t start, const uint8_t* leaves, uint64_t n, const uint8_t* left_boundary,
+                               const uint8_t* zeros, uint8_t* out_nodes) {
+    OG_ENTER(ctx);
+    if (!ctx || !leaves || !left_boundary || !zeros || !out_nodes || depth == 0 || depth > 32 || n == 0 || n > (1ull << 28)) return OG_E_INVALID;
+    if (start + n > (1ull << depth)) return OG_E_INVALID;
+    uint64_t total = 0;
+    for (uint32_t l = 1; l <= depth; l++) total += ((start + n - 1) >> l) - (start >> l) + 1;
+    Fr aux[64];
+    for (uint32_t l = 0; l < depth; l++)
+        if (!host_load(aux[l], left_boundary + 32 * l) || !host_load(aux[depth + l], zeros + 32 * l)) return OG_E_ENCODING;
+    OG_SLOT(ctx, din, uint8_t, S_IO_A, 32 * n);
+    OG_SLOT(ctx, nodes, Fr, S_IO_B, sizeof(Fr) * (n + total));
+    OG_SLOT(ctx, dout, uint8_t, S_IO_C, 32 * total);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, din, leaves, 32 * n);
+    OG_TRY(mimc_to_mont_dev(ctx, din, n, nodes));
+    OG_TRY(mimc_tree_append_dev(ctx, depth, start, n, aux, nodes));
+    OG_TRY(mimc_from_mont_dev(ctx, nodes + n, total, dout));
+    D2H(ctx, out_nodes, dout, 32 * total);
+    return check_flag(ctx);
+}
+
 // ---- BabyJubJub (the reference's own signature scheme, babyjubjub/mod.rs) -----------------------------------
 int32_t og_bjj_verify_batch(og_ctx* ctx, const uint8_t* pk_x, const uint8_t* pk_is_odd, const uint8_t* messages, const uint8_t* signatures,
                             uint32_t n, int32_t hash_kind, uint8_t* out_status) {
@@ -609,6 +658,33 @@ int32_t og_g2_sum(og_ctx* ctx, const uint8_t* points, uint64_t n, uint8_t* out12
     OG_TRY(sum_g2_dev(ctx, dp, n, dout));
     D2H(ctx, out128, dout, 128);
     return check_flag(ctx);
+}
+
+int32_t og_g1_sum_dev(og_ctx* ctx, const uint8_t* d_points, uint64_t n, uint8_t* d_out64) {
+    OG_ENTER(ctx);
+    if (!d_out64 || (n && !d_points)) return OG_E_INVALID;
+    return sum_g1_dev(ctx, d_points, n, d_out64);
+}
+int32_t og_g2_sum_dev(og_ctx* ctx, const uint8_t* d_points, uint64_t n, uint8_t* d_out128) {
+    OG_ENTER(ctx);
+    if (!d_out128 || (n && !d_points)) return OG_E_INVALID;
+    return sum_g2_dev(ctx, d_points, n, d_out128);
+}
+int32_t og_g1_generator_mul_dev(og_ctx* ctx, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out_points) {
+    OG_ENTER(ctx);
+    if (n && (!d_scalars || !d_out_points)) return OG_E_INVALID;
+    if (n == 0) return OG_OK;
+    OG_SLOT(ctx, dp, G1Affine, S_IO_B, sizeof(G1Affine) * n);
+    OG_TRY(fixed_base_mul_g1(ctx, d_scalars, n, dp));
+    return g1_mont_to_bytes(ctx, dp, n, d_out_points);
+}
+int32_t og_g2_generator_mul_dev(og_ctx* ctx, const uint8_t* d_scalars, uint64_t n, uint8_t* d_out_points) {
+    OG_ENTER(ctx);
+    if (n && (!d_scalars || !d_out_points)) return OG_E_INVALID;
+    if (n == 0) return OG_OK;
+    OG_SLOT(ctx, dp, G2Affine, S_IO_B, sizeof(G2Affine) * n);
+    OG_TRY(fixed_base_mul_g2(ctx, d_scalars, n, dp));
+    return g2_mont_to_bytes(ctx, dp, n, d_out_points);
 }
 
 // out[i] = scalars[i] * G (fixed-base, generator of G1 / G2): used by the setup and to synthesise MSM inputs

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) k_public_out(const Fr* __restrict__ W, ui
 using namespace og;
 
 struct og_pk {
-    og_ctx* ctx = nullptr;
+    int device = -1;                     // the GPU the tables live on (a key is bound to the device it was loaded on)
     uint32_t depth = 0, n_constraints = 0, n_vars = 0, n_pub = 0, log_m = 0;
     uint32_t n_supp = 0;                 // |{i : B_query[i] != infinity}|
     // window size per MSM: index 0 = A (G1), 1 = B (G2), 2 = C' (G1); nb = 2^(c-1) buckets per proof
@@ -173,7 +173,6 @@ struct og_pk {
     Fr *a_val = nullptr, *b_val = nullptr;
     G1Affine *tabA = nullptr, *tabC = nullptr;
     G2Affine* tabB = nullptr;
-    std::vector<uint8_t> vk_hint;        // unused; reserved
 };
 
 namespace og {
@@ -223,6 +222,7 @@ static int32_t upload_csr(og_ctx* ctx, Reader& rd, uint32_t n_rows, uint32_t n_v
 
 void pk_free(og_pk* pk) {
     if (!pk) return;
+    if (pk->device >= 0) cudaSetDevice(pk->device);    // the key may outlive the context that loaded it
     cudaFree(pk->a_ptr); cudaFree(pk->a_col); cudaFree(pk->b_ptr); cudaFree(pk->b_col); cudaFree(pk->supp);
     cudaFree(pk->a_val); cudaFree(pk->b_val); cudaFree(pk->tabA); cudaFree(pk->tabC); cudaFree(pk->tabB);
     delete pk;
@@ -234,9 +234,9 @@ int32_t pk_load(og_ctx* ctx, const uint8_t* bytes, uint64_t len, og_pk** out) {
     if (!magic || memcmp(magic, "OGPK", 4) != 0) return OG_E_ENCODING;
     if (rd.u32() != 1) return OG_E_ENCODING;
     og_pk* pk = new og_pk();
-    pk->ctx = ctx;
+    pk->device = ctx->device;
     pk->depth = rd.u32(); pk->n_constraints = rd.u32(); pk->n_vars = rd.u32(); pk->n_pub = rd.u32(); pk->log_m = rd.u32();
-    if (!rd.ok || pk->log_m > 24 || pk->n_vars == 0 || pk->n_pub + 1 > pk->n_vars ||
+    if (!rd.ok || pk->log_m > 24 || pk->n_vars == 0 || pk->n_pub > (1u << 16) || pk->n_pub + 1 > pk->n_vars ||
         (uint64_t)pk->n_constraints + pk->n_pub + 1 > (1ull << pk->log_m)) { delete pk; return OG_E_ENCODING; }
     const uint32_t nv = pk->n_vars, n_priv = nv - pk->n_pub - 1, m = 1u << pk->log_m;
     const uint8_t* alpha1 = rd.take(64); const uint8_t* beta1 = rd.take(64); const uint8_t* beta2 = rd.take(128);
@@ -313,7 +313,7 @@ int32_t pk_load(og_ctx* ctx, const uint8_t* bytes, uint64_t len, og_pk** out) {
     return OG_OK;
 }
 
-bool pk_on_device_of(const og_pk* pk, const og_ctx* ctx) { return pk && ctx && pk->ctx && pk->ctx->device == ctx->device; }
+bool pk_on_device_of(const og_pk* pk, const og_ctx* ctx) { return pk && ctx && pk->device == ctx->device; }
 
 void pk_info(const og_pk* pk, uint32_t* n_vars, uint32_t* n_pub, uint32_t* log_m, uint32_t* depth) {
     if (n_vars) *n_vars = pk->n_vars;
@@ -323,6 +323,9 @@ void pk_info(const og_pk* pk, uint32_t* n_vars, uint32_t* n_pub, uint32_t* log_m
 }
 
 // ---- the prover ---------------------------------------------------------------------------------------------
+// A batch is cut into chunks of CB proofs; up to MAX_LANES chunks are in flight, each lane with its own scratch
+// and its own pair of streams (common.cuh): the short latency-bound kernels of one chunk (witness chains, sort,
+// scan, NTT, bucket reduction, final s*A) run under the issue-bound bucket accumulation of the other.
 struct ChunkBufs {
     Fr *W, *rs_m, *abc, *ntt_tmp, *bsc, *csc;
     uint32_t *counts, *offsets, *cursor, *sorted, *heavy;
@@ -331,26 +334,26 @@ struct ChunkBufs {
     uint32_t w_stride, bsc_stride, csc_stride;
 };
 
-// W, rs_m and the per-proof totals cover the whole batch (the sequential witness chain and the final
-// s*A are latency-bound per thread, so they run once per batch); everything else is per chunk of B proofs.
-static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_t B, ChunkBufs& b) {
+// W, rs_m and the per-proof totals cover the whole batch; everything else is per chunk of B proofs and per lane
+static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_t B, int lane, ChunkBufs& b) {
     const uint32_t m = 1u << pk->log_m;
     b.w_stride = pk->n_vars + 2;
     b.bsc_stride = pk->nB;
     b.csc_stride = pk->nC;
     size_t max_pts = pk->nC > pk->nA ? pk->nC : pk->nA;
     size_t n_keys = (size_t)B * pk->max_nb;
+    auto S = [&](int id0, int id1) { return lane ? id1 : id0; };
     b.W = (Fr*)ctx->slot(S_PR_WIT, sizeof(Fr) * (size_t)batch * b.w_stride);
     b.rs_m = (Fr*)ctx->slot(S_PR_MISC, sizeof(Fr) * 2 * (size_t)batch);
-    b.abc = (Fr*)ctx->slot(S_PR_ABC, sizeof(Fr) * (size_t)B * 3 * m * 2);
-    b.bsc = (Fr*)ctx->slot(S_PR_SCALARS, sizeof(Fr) * (size_t)B * (b.bsc_stride + b.csc_stride));
-    b.sorted = (uint32_t*)ctx->slot(S_PR_SORTED, 4 * (size_t)B * max_pts * pk->max_windows);
-    b.counts = (uint32_t*)ctx->slot(S_PR_COUNTS, 4 * n_keys);
-    b.offsets = (uint32_t*)ctx->slot(S_PR_OFFSETS, 4 * (n_keys + 1));
-    b.cursor = (uint32_t*)ctx->slot(S_PR_CURSOR, 4 * n_keys);
-    b.heavy = (uint32_t*)ctx->slot(S_PR_HEAVY, 4 * (n_keys + 1));
-    b.bk2 = (G2XYZZ*)ctx->slot(S_PR_BUCKETS, sizeof(G2XYZZ) * n_keys);
-    b.lvl2 = (G2XYZZ*)ctx->slot(S_PR_SEG, sizeof(G2XYZZ) * msm_lvl_elems(B, pk->max_nb));
+    b.abc = (Fr*)ctx->slot(S(S_PR_ABC, S_L1_ABC), sizeof(Fr) * (size_t)B * 3 * m * 2);
+    b.bsc = (Fr*)ctx->slot(S(S_PR_SCALARS, S_L1_SCALARS), sizeof(Fr) * (size_t)B * (b.bsc_stride + b.csc_stride));
+    b.sorted = (uint32_t*)ctx->slot(S(S_PR_SORTED, S_L1_SORTED), 4 * (size_t)B * max_pts * pk->max_windows);
+    b.counts = (uint32_t*)ctx->slot(S(S_PR_COUNTS, S_L1_COUNTS), 4 * n_keys);
+    b.offsets = (uint32_t*)ctx->slot(S(S_PR_OFFSETS, S_L1_OFFSETS), 4 * (n_keys + 1));
+    b.cursor = (uint32_t*)ctx->slot(S(S_PR_CURSOR, S_L1_CURSOR), 4 * n_keys);
+    b.heavy = (uint32_t*)ctx->slot(S(S_PR_HEAVY, S_L1_HEAVY), 4 * (n_keys + 1));
+    b.bk2 = (G2XYZZ*)ctx->slot(S(S_PR_BUCKETS, S_L1_BUCKETS), sizeof(G2XYZZ) * n_keys);
+    b.lvl2 = (G2XYZZ*)ctx->slot(S(S_PR_SEG, S_L1_SEG), sizeof(G2XYZZ) * msm_lvl_elems(B, pk->max_nb));
     b.totA = (G1XYZZ*)ctx->slot(S_PR_SUMS, (sizeof(G1XYZZ) * 2 + sizeof(G2XYZZ)) * (size_t)batch);
     if (!b.W || !b.rs_m || !b.abc || !b.bsc || !b.sorted || !b.counts || !b.offsets || !b.cursor || !b.heavy || !b.bk2 || !b.lvl2 || !b.totA)
         return OG_E_NOMEM;
@@ -388,11 +391,30 @@ static int32_t run_msm_g2(og_ctx* ctx, const og_pk* pk, int which, ChunkBufs& b,
     return msm_buckets_g2(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb[which], (uint64_t)B * n_pts * pk->n_windows[which], b.bk2, b.lvl2, b.heavy, b.cursor, totals);
 }
 
-// proofs [off, off+B): everything between the witness rows (already in b.W) and the per-proof MSM totals
-static int32_t prove_chunk(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t off, uint32_t B) {
+// where a chunk's witness rows come from
+struct WitnessSource {
+    const uint8_t *d_null = nullptr, *d_sec = nullptr, *d_rec = nullptr, *d_sib = nullptr;   // secret inputs (prove_withdraw)
+    const uint32_t* d_bits = nullptr;
+    const uint8_t* d_wit = nullptr;                                                         // or full witnesses (prove)
+    uint8_t* d_public = nullptr;
+};
+
+// proofs [off, off+B) on the current stream: witness rows -> per-proof MSM totals -> proof bytes
+static int32_t prove_chunk(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, const WitnessSource& src, uint32_t off, uint32_t B,
+                           const uint8_t* d_rs, uint8_t* d_proofs) {
     const uint32_t m = 1u << pk->log_m, n_priv = pk->n_vars - pk->n_pub - 1;
-    const Fr* W = b.W + (size_t)off * b.w_stride;
-    const Fr* rs_m = b.rs_m + 2 * (size_t)off;
+    Fr* W = b.W + (size_t)off * b.w_stride;
+    Fr* rs_m = b.rs_m + 2 * (size_t)off;
+    if (src.d_wit) {
+        uint64_t tot = (uint64_t)B * pk->n_vars;
+        OG_LAUNCH(ctx, k_witness_in, (unsigned)((tot + 127) / 128), 128, 0, src.d_wit + 32ull * off * pk->n_vars, B, pk->n_vars, b.w_stride, W, ctx->d_flag);
+    } else {
+        WithdrawLayout L = WithdrawLayout::make(pk->depth);
+        OG_TRY(withdraw_witness_strided_dev(ctx, L, b.w_stride, src.d_null + 32ull * off, src.d_sec + 32ull * off, src.d_rec + 32ull * off,
+                                            src.d_sib + 32ull * off * pk->depth, src.d_bits + off, B, W));
+        if (src.d_public) OG_LAUNCH(ctx, k_public_out, (B * pk->n_pub + 127) / 128, 128, 0, W, b.w_stride, B, pk->n_pub, src.d_public + 32ull * off * pk->n_pub);
+    }
+    OG_LAUNCH(ctx, k_extras, (B + 127) / 128, 128, 0, d_rs + 64ull * off, B, pk->n_vars, b.w_stride, W, rs_m, ctx->d_flag);
     CsrDev A{pk->a_ptr, pk->a_col, pk->a_val}, Bm{pk->b_ptr, pk->b_col, pk->b_val};
     OG_LAUNCH(ctx, k_abc, dim3((m + 127) / 128, B), 128, 0, A, Bm, pk->n_constraints, pk->n_pub, pk->log_m, W, b.w_stride, B, b.abc);
     OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3 * B, 1, 0));
@@ -404,18 +426,8 @@ static int32_t prove_chunk(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t 
     OG_TRY(run_msm_g1(ctx, pk, 0, b, B, pk->tabA, pk->nA, W, b.w_stride, b.totA + off));
     OG_TRY(run_msm_g1(ctx, pk, 2, b, B, pk->tabC, pk->nC, b.csc, b.csc_stride, b.totC + off));
     OG_TRY(run_msm_g2(ctx, pk, 1, b, B, pk->tabB, pk->nB, b.bsc, b.bsc_stride, b.totB + off));
-    return OG_OK;
-}
-
-// whole batch: extras before the chunks, assembly after them
-static int32_t prove_batch(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, uint32_t batch, uint32_t CB, const uint8_t* d_rs, uint8_t* d_proofs) {
-    OG_LAUNCH(ctx, k_extras, (batch + 127) / 128, 128, 0, d_rs, batch, pk->n_vars, b.w_stride, b.W, b.rs_m, ctx->d_flag);
-    for (uint32_t off = 0; off < batch; off += CB) {
-        uint32_t B = batch - off < CB ? batch - off : CB;
-        OG_TRY(prove_chunk(ctx, pk, b, off, B));
-    }
-    OG_LAUNCH(ctx, k_assemble_g1, (batch + 31) / 32, 32, 0, b.totA, b.totC, b.rs_m, batch, d_proofs);
-    OG_LAUNCH(ctx, k_assemble_g2, (batch + 31) / 32, 32, 0, b.totB, batch, d_proofs);
+    OG_LAUNCH(ctx, k_assemble_g1, (B + 31) / 32, 32, 0, b.totA + off, b.totC + off, rs_m, B, d_proofs + 256ull * off);
+    OG_LAUNCH(ctx, k_assemble_g2, (B + 31) / 32, 32, 0, b.totB + off, B, d_proofs + 256ull * off);
     return OG_OK;
 }
 
@@ -428,9 +440,42 @@ static uint32_t chunk_limit(const og_pk* pk) {
     return (uint32_t)(lim < 1 ? 1 : lim);
 }
 
-static uint32_t chunk_size(uint32_t batch) {
-    uint32_t c = env_u32("OG_CHUNK", 1024);   // ~28 GB of scratch at 1024 proofs; measured 2037 / 2076 / 2093 proofs/s at 256 / 512 / 1024
+// OG_CHUNK proofs per chunk (default 1024 = the whole BASELINE batch, ~28 GB of scratch per lane; profiles/r2_lanes_sweep.md), OG_LANES chunks in flight (default 2, 1 = serial)
+static uint32_t chunk_size(const og_pk* pk, uint32_t batch) {
+    uint32_t c = env_u32("OG_CHUNK", 1024);
+    if (c > chunk_limit(pk)) c = chunk_limit(pk);
     return c < batch ? c : batch;
+}
+
+static int32_t prove_batch(og_ctx* ctx, const og_pk* pk, const WitnessSource& src, uint32_t batch, const uint8_t* d_rs, uint8_t* d_proofs) {
+    const uint32_t CB = chunk_size(pk, batch);
+    const uint32_t n_chunks = (batch + CB - 1) / CB;
+    uint32_t lanes = env_u32("OG_LANES", MAX_LANES);
+    if (lanes > (uint32_t)MAX_LANES) lanes = MAX_LANES;
+    if (lanes > n_chunks) lanes = n_chunks;
+    ChunkBufs bufs[MAX_LANES];
+    for (uint32_t l = 0; l < lanes; l++) OG_TRY(alloc_chunk(ctx, pk, batch, CB, (int)l, bufs[l]));
+    OG_TRY(ntt_prepare(ctx, pk->log_m));
+    cudaStream_t main_s = ctx->stream;
+    if (lanes <= 1) {
+        for (uint32_t off = 0; off < batch; off += CB) OG_TRY(prove_chunk(ctx, pk, bufs[0], src, off, batch - off < CB ? batch - off : CB, d_rs, d_proofs));
+        return OG_OK;
+    }
+    OG_CUDA(ctx, cudaEventRecord(ctx->fork_ev, main_s));
+    for (uint32_t l = 0; l < lanes; l++) OG_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_hi[l], ctx->fork_ev, 0));
+    int32_t rc = OG_OK;
+    for (uint32_t c = 0; c < n_chunks && rc == OG_OK; c++) {
+        uint32_t l = c % lanes, off = c * CB;
+        ctx->lane = (int)l; ctx->stream = ctx->lane_hi[l]; ctx->acc_stream = ctx->lane_lo[l];
+        rc = prove_chunk(ctx, pk, bufs[l], src, off, batch - off < CB ? batch - off : CB, d_rs, d_proofs);
+    }
+    ctx->lane = 0; ctx->stream = main_s; ctx->acc_stream = nullptr;
+    // join: whatever was enqueued must finish before the caller's stream goes on (also on the error path)
+    for (uint32_t l = 0; l < lanes; l++) {
+        cudaError_t e = stream_handoff(ctx->lane_ev[l], ctx->lane_hi[l], main_s);
+        if (e != cudaSuccess && rc == OG_OK) { snprintf(ctx->err, sizeof(ctx->err), "lane join: %s", cudaGetErrorString(e)); rc = OG_E_CUDA; }
+    }
+    return rc;
 }
 
 int32_t prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_null, const uint8_t* d_sec, const uint8_t* d_rec,
@@ -440,30 +485,22 @@ int32_t prove_withdraw_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_null, 
     if (batch == 0) return OG_OK;
     WithdrawLayout L = WithdrawLayout::make(pk->depth);
     if (L.n_vars != pk->n_vars) return OG_E_INVALID;
-    uint32_t CB = chunk_size(batch);
-    if (CB > chunk_limit(pk)) CB = chunk_limit(pk);
-    ChunkBufs b;
-    OG_TRY(alloc_chunk(ctx, pk, batch, CB, b));
-    OG_TRY(withdraw_witness_strided_dev(ctx, L, b.w_stride, d_null, d_sec, d_rec, d_sib, d_bits, batch, b.W));
-    if (d_public) OG_LAUNCH(ctx, k_public_out, (batch * pk->n_pub + 127) / 128, 128, 0, b.W, b.w_stride, batch, pk->n_pub, d_public);
-    return prove_batch(ctx, pk, b, batch, CB, d_rs, d_proofs);
+    WitnessSource src;
+    src.d_null = d_null; src.d_sec = d_sec; src.d_rec = d_rec; src.d_sib = d_sib; src.d_bits = d_bits; src.d_public = d_public;
+    return prove_batch(ctx, pk, src, batch, d_rs, d_proofs);
 }
 
 int32_t prove_witness_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_wit, uint32_t batch, const uint8_t* d_rs, uint8_t* d_proofs) {
     if (batch == 0) return OG_OK;
-    uint32_t CB = chunk_size(batch);
-    if (CB > chunk_limit(pk)) CB = chunk_limit(pk);
-    ChunkBufs b;
-    OG_TRY(alloc_chunk(ctx, pk, batch, CB, b));
-    uint64_t tot = (uint64_t)batch * pk->n_vars;
-    OG_LAUNCH(ctx, k_witness_in, (unsigned)((tot + 127) / 128), 128, 0, d_wit, batch, pk->n_vars, b.w_stride, b.W, ctx->d_flag);
-    return prove_batch(ctx, pk, b, batch, CB, d_rs, d_proofs);
+    WitnessSource src;
+    src.d_wit = d_wit;
+    return prove_batch(ctx, pk, src, batch, d_rs, d_proofs);
 }
 
 // debug / parity probe: d_j for one witness (canonical bytes on device in and out)
 int32_t h_evals_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_wit, uint8_t* d_out) {
     ChunkBufs b;
-    OG_TRY(alloc_chunk(ctx, pk, 1, 1, b));
+    OG_TRY(alloc_chunk(ctx, pk, 1, 1, 0, b));
     const uint32_t m = 1u << pk->log_m, n_priv = pk->n_vars - pk->n_pub - 1;
     OG_LAUNCH(ctx, k_witness_in, (pk->n_vars + 127) / 128, 128, 0, d_wit, 1, pk->n_vars, b.w_stride, b.W, ctx->d_flag);
     CsrDev A{pk->a_ptr, pk->a_col, pk->a_val}, Bm{pk->b_ptr, pk->b_col, pk->b_val};

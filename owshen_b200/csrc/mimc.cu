@@ -70,6 +70,19 @@ __global__ void __launch_bounds__(64) k_tree_level(const Fr* __restrict__ in, ui
     out[i] = mimc7_hash2<false>(in[2 * i], in[2 * i + 1], nullptr, nullptr);
 }
 
+// one level of an APPEND to a fixed-depth sparse tree: parents [p0, p0 + n_out) of the dirty children [c0, c0 + n_in).
+// A child left of the dirty range is the stored boundary node of this level (at most one: index c0 - 1), a child right
+// of it is the empty-subtree root of the level (append-only: nothing exists to the right of the new leaves).
+__global__ void __launch_bounds__(64) k_tree_append_level(const Fr* __restrict__ in, uint64_t c0, uint64_t n_in, uint64_t p0, uint64_t n_out,
+                                                          Fr left_boundary, Fr zero, Fr* __restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    uint64_t l = 2 * (p0 + i), r = l + 1;
+    Fr a = l < c0 ? left_boundary : (l < c0 + n_in ? in[l - c0] : zero);
+    Fr b = r < c0 ? left_boundary : (r < c0 + n_in ? in[r - c0] : zero);
+    out[i] = mimc7_hash2<false>(a, b, nullptr, nullptr);
+}
+
 __global__ void __launch_bounds__(128) k_to_mont(const uint8_t* __restrict__ in, uint64_t n, Fr* __restrict__ out, int* flag) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = load_canonical<Fr>(in + 32 * i, flag);
@@ -158,8 +171,7 @@ int32_t mimc_hash2_dev(og_ctx* ctx, const uint8_t* d_l, const uint8_t* d_r, uint
 int32_t mimc_merkle_paths_dev(og_ctx* ctx, const uint8_t* d_leaves, const uint8_t* d_siblings, const uint32_t* d_bits,
                               uint32_t n_paths, uint32_t depth, uint8_t* d_out) {
     if (n_paths == 0) return OG_OK;
-    static const unsigned lanes = [] { const char* v = getenv("OG_MIMC_LANES"); int x = v ? atoi(v) : 32; return (unsigned)(x >= 1 && x <= 32 ? x : 32); }();
-    OG_LAUNCH(ctx, k_merkle_paths, (n_paths + lanes - 1) / lanes, lanes, 0, d_leaves, d_siblings, d_bits, n_paths, depth, d_out, ctx->d_flag);
+    OG_LAUNCH(ctx, k_merkle_paths, (n_paths + 31) / 32, 32, 0, d_leaves, d_siblings, d_bits, n_paths, depth, d_out, ctx->d_flag);
     return OG_OK;
 }
 
@@ -181,6 +193,20 @@ int32_t mimc_tree_build_dev(og_ctx* ctx, Fr* d_levels, uint64_t n_leaves) {
         Fr* out = in + n;
         OG_LAUNCH(ctx, k_tree_level, (unsigned)((n / 2 + 63) / 64), 64, 0, in, n / 2, out);
         in = out;
+    }
+    return OG_OK;
+}
+
+// d_nodes: Montgomery buffer, level 0 (the n new leaves) already filled; levels 1..depth are appended behind it.
+// h_aux (host): 2*depth Montgomery elements = left boundary per level, then empty-subtree root per level (kernel arguments).
+int32_t mimc_tree_append_dev(og_ctx* ctx, uint32_t depth, uint64_t start, uint64_t n, const Fr* h_aux, Fr* d_nodes) {
+    Fr* in = d_nodes;
+    uint64_t c0 = start, n_in = n;
+    for (uint32_t l = 0; l < depth; l++) {
+        uint64_t p0 = c0 >> 1, p1 = (c0 + n_in - 1) >> 1, n_out = p1 - p0 + 1;
+        Fr* out = in + n_in;
+        OG_LAUNCH(ctx, k_tree_append_level, (unsigned)((n_out + 63) / 64), 64, 0, in, c0, n_in, p0, n_out, h_aux[l], h_aux[depth + l], out);
+        in = out; c0 = p0; n_in = n_out;
     }
     return OG_OK;
 }

@@ -140,17 +140,15 @@ __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restric
     });
 }
 
-// Tiled variant for groups with nb <= 4096 buckets (the batched prover: one group per proof).  A CTA owns a
-// tile of one problem's scalars, histograms its digits in shared memory and touches global memory once per
-// bucket instead of once per digit (5-20x fewer global atomics); in the scatter pass it reserves a contiguous
-// run per bucket, so the 4-byte entries of a tile land in runs instead of isolated sectors.
-constexpr uint32_t DIG_TILE = 4096, DIG_THREADS = 256, DIG_MAX_NB = 4096, DIG_MAX_NB_COUNT = 32768;
+// Tiled histogram for the batched prover (one group per proof, nb <= 32768): a CTA owns a tile of one problem's
+// scalars, counts its digits in shared memory and touches global memory once per bucket instead of once per
+// digit (5x faster than global atomics: 5 vs 24 ms per 1024 proofs).  The scatter stays the plain k_digits<true>:
+// a tiled scatter with run reservation and a one-CTA-per-proof shared-memory sort were both measured slower
+// (39 vs 33 ms and 56.6 vs 29 ms per 1024 proofs, profiles/r1_*; their code was removed in round 2).
+constexpr uint32_t DIG_TILE = 4096, DIG_THREADS = 256, DIG_MAX_NB_COUNT = 32768;
 
-template <bool SCATTER>
-__global__ void __launch_bounds__(DIG_THREADS) k_digits_tiled(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
-                                                              uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
-    extern __shared__ uint32_t hist[];                    // nb counters (dynamic: up to 128 KB in the count pass)
-    __shared__ uint32_t base[SCATTER ? DIG_MAX_NB : 1];
+__global__ void __launch_bounds__(DIG_THREADS) k_digits_count_tiled(DigitPlan P, uint32_t* __restrict__ counts, int* flag) {
+    extern __shared__ uint32_t hist[];                    // nb counters (dynamic: up to 128 KB)
     const uint32_t prob = blockIdx.y, nb = P.nb;
     const uint64_t lo = (uint64_t)blockIdx.x * DIG_TILE;
     const uint64_t hi = lo + DIG_TILE < P.n ? lo + DIG_TILE : P.n;
@@ -162,76 +160,7 @@ __global__ void __launch_bounds__(DIG_THREADS) k_digits_tiled(DigitPlan P, uint3
         if (it.load(P, prob, i, flag)) it.for_each(P, [&](uint32_t, uint32_t b, uint32_t) { atomicAdd(&hist[b], 1u); });
     }
     __syncthreads();
-    if constexpr (!SCATTER) {
-        for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) if (hist[b]) atomicAdd(&counts[key0 + b], hist[b]);
-    } else {
-    for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) {
-        uint32_t h = hist[b];
-        base[b] = h ? atomicAdd(&cursor[key0 + b], h) : 0;
-        hist[b] = 0;                                                  // reused as the running rank inside the run
-    }
-    __syncthreads();
-    for (uint64_t i = lo + threadIdx.x; i < hi; i += DIG_THREADS) {
-        DigitIter it;
-        if (it.load(P, prob, i, flag))
-            it.for_each(P, [&](uint32_t w, uint32_t b, uint32_t neg) {
-                uint32_t pos = base[b] + atomicAdd(&hist[b], 1u);
-                sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
-            });
-    }
-    }
-}
-
-// ---- one-CTA-per-group counting sort (the batched prover: one group per proof, nb <= 32768) ------------------
-// The whole histogram of a proof's MSM lives in shared memory (4 * nb bytes, up to 128 KB): count, scan and scatter
-// run in ONE kernel with shared-memory atomics only -- no global atomics, no separate scan.  Every group owns a
-// fixed-stride region of the sorted array (stride = points * windows, the most entries it can produce), so no
-// offsets cross groups.  An experiment that lost: see msm_sort_digits.
-constexpr uint32_t SORT_THREADS = 1024, SORT_MAX_NB = 32768;
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_group(DigitPlan P, uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                                             uint32_t* __restrict__ sorted, uint32_t stride, int* flag) {
-    extern __shared__ uint32_t cnt[];                 // nb counters, then reused as write cursors
-    __shared__ uint32_t part[SORT_THREADS];
-    const uint32_t prob = blockIdx.x, nb = P.nb, t = threadIdx.x;
-    const uint32_t key0 = prob * nb;
-    for (uint32_t b = t; b < nb; b += SORT_THREADS) cnt[b] = 0;
-    __syncthreads();
-    for (uint64_t i = t; i < P.n; i += SORT_THREADS) {
-        DigitIter it;
-        if (it.load(P, prob, i, flag)) it.for_each(P, [&](uint32_t, uint32_t b, uint32_t) { atomicAdd(&cnt[b], 1u); });
-    }
-    __syncthreads();
-    // exclusive scan: thread t owns the consecutive counters [t*per, (t+1)*per)
-    const uint32_t per = (nb + SORT_THREADS - 1) / SORT_THREADS;
-    const uint32_t lo = min(nb, t * per), hi = min(nb, lo + per);
-    uint32_t sum = 0;
-    for (uint32_t b = lo; b < hi; b++) sum += cnt[b];
-    part[t] = sum;
-    __syncthreads();
-    for (uint32_t d = 1; d < SORT_THREADS; d <<= 1) {
-        uint32_t v = t >= d ? part[t - d] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    uint32_t run = t ? part[t - 1] : 0;
-    const uint32_t base = prob * stride;
-    for (uint32_t b = lo; b < hi; b++) {
-        uint32_t c = cnt[b];
-        counts[key0 + b] = c;
-        offsets[key0 + b] = base + run;
-        cnt[b] = run;                                   // cursor, local to the group's region
-        run += c;
-    }
-    __syncthreads();
-    for (uint64_t i = t; i < P.n; i += SORT_THREADS) {
-        DigitIter it;
-        if (it.load(P, prob, i, flag))
-            it.for_each(P, [&](uint32_t w, uint32_t b, uint32_t neg) {
-                uint32_t pos = atomicAdd(&cnt[b], 1u);
-                sorted[base + pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
-            });
-    }
+    for (uint32_t b = threadIdx.x; b < nb; b += DIG_THREADS) if (hist[b]) atomicAdd(&counts[key0 + b], hist[b]);
 }
 
 // ---- 2: exclusive scan: tile sums -> scan of the tile sums (one CTA) -> tile rescan with offsets ----------
@@ -297,20 +226,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
 
 int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uint32_t* d_counts, uint32_t* d_offsets,
                         uint32_t* d_cursor, uint32_t* d_sorted) {
-    // measured slower than the tiled count + global scatter below (56.6 vs 29 ms per 1024 proofs): shared-memory
-    // atomics on random addresses run at ~2 cycles per lane and 128 KB of histogram allow one CTA per SM; kept for
-    // reference behind OG_GROUP_SORT=1
-    static const int group_sort = [] { const char* v = getenv("OG_GROUP_SORT"); return v ? atoi(v) : 0; }();
-    const uint64_t gstride = plan.n * plan.n_windows;
-    if (group_sort && plan.key_stride_window == 0 && plan.key_stride_problem == 1 && plan.nb <= SORT_MAX_NB && plan.n > 0 &&
-        plan.n_problems > 0 && gstride * plan.n_problems < 0xFFFFFFFFull) {
-        if (!ctx->sort_smem_opt_in) {
-            OG_CUDA(ctx, cudaFuncSetAttribute(k_sort_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * SORT_MAX_NB)));
-            ctx->sort_smem_opt_in = true;
-        }
-        OG_LAUNCH(ctx, k_sort_group, plan.n_problems, SORT_THREADS, 4 * (size_t)plan.nb, plan, d_counts, d_offsets, d_sorted, (uint32_t)gstride, ctx->d_flag);
-        return OG_OK;
-    }
     OG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)n_keys, ctx->stream));
     if (plan.n == 0 || plan.n_problems == 0) {
         OG_CUDA(ctx, cudaMemsetAsync(d_offsets, 0, sizeof(uint32_t) * ((size_t)n_keys + 1), ctx->stream));
@@ -318,25 +233,21 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
     }
     const bool tiled = plan.key_stride_window == 0 && plan.nb <= DIG_MAX_NB_COUNT;
     if (tiled && !ctx->digits_smem_opt_in) {      // per device, hence per context
-        OG_CUDA(ctx, cudaFuncSetAttribute(k_digits_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * DIG_MAX_NB_COUNT)));
+        OG_CUDA(ctx, cudaFuncSetAttribute(k_digits_count_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * DIG_MAX_NB_COUNT)));
         ctx->digits_smem_opt_in = true;
     }
     dim3 grid((unsigned)((plan.n + 255) / 256), plan.n_problems);
     dim3 tgrid((unsigned)((plan.n + DIG_TILE - 1) / DIG_TILE), plan.n_problems);
-    if (tiled) OG_LAUNCHN(ctx, "k_digits_tiled<count>", k_digits_tiled<false>, tgrid, DIG_THREADS, 4 * (size_t)plan.nb, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
-    else OG_LAUNCH(ctx, k_digits<false>, grid, 256, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
+    if (tiled) OG_LAUNCH(ctx, k_digits_count_tiled, tgrid, DIG_THREADS, 4 * (size_t)plan.nb, plan, d_counts, ctx->d_flag);
+    else OG_LAUNCHN(ctx, "k_digits_count", k_digits<false>, grid, 256, 0, plan, d_counts, nullptr, nullptr, nullptr, ctx->d_flag);
     {   // offsets[n_keys] receives the grand total; cursor[k] = offsets[k] for the scatter
         uint32_t n_tiles = (n_keys + SCAN_TILE - 1) / SCAN_TILE;
-        OG_SLOT(ctx, tile_sums, uint32_t, S_MSM_MISC, 4 * (size_t)n_tiles);
+        OG_SLOT(ctx, tile_sums, uint32_t, ctx->lane ? S_L1_MSM_MISC : S_MSM_MISC, 4 * (size_t)n_tiles);
         OG_LAUNCH(ctx, k_scan_tiles, n_tiles, SCAN_THREADS, 0, d_counts, n_keys, tile_sums);
         OG_LAUNCH(ctx, k_scan_tile_sums, 1, SCAN_THREADS, 0, tile_sums, n_tiles, d_offsets + n_keys);
         OG_LAUNCH(ctx, k_scan_apply, n_tiles, SCAN_THREADS, 0, d_counts, n_keys, tile_sums, d_offsets, d_cursor);
     }
-    // measured: the tiled scatter (run reservation + shared-memory ranks) is slower than the plain one
-    // (39 vs 33 ms per 1024 proofs) while the tiled count is 5x faster (5 vs 24 ms) -> tiled count, plain scatter
-    static const int tiled_scatter = [] { const char* v = getenv("OG_TILED_SCATTER"); return v ? atoi(v) : 0; }();
-    if (tiled && tiled_scatter && plan.nb <= DIG_MAX_NB) OG_LAUNCHN(ctx, "k_digits_tiled<scatter>", k_digits_tiled<true>, tgrid, DIG_THREADS, 4 * (size_t)plan.nb, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
-    else OG_LAUNCH(ctx, k_digits<true>, grid, 256, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
+    OG_LAUNCHN(ctx, "k_digits_scatter", k_digits<true>, grid, 256, 0, plan, d_counts, d_offsets, d_cursor, d_sorted, ctx->d_flag);
     return OG_OK;
 }
 #endif  // OG_MSM_G1
@@ -385,47 +296,6 @@ __device__ __forceinline__ Affine<F> fetch_point(const Affine<F>* __restrict__ t
     return p;
 }
 
-// MINB = minimum resident CTAs per SM requested from ptxas: trades registers (spills) for warps in flight;
-// the kernel is latency-bound on carry chains, so the best point is measured, not guessed (OG_ACC_OCC).
-template <class F, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_bucket_acc(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
-                                                    const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
-                                                    uint32_t n_keys, uint32_t cap, XYZZ<F>* __restrict__ buckets,
-                                                    uint32_t* __restrict__ heavy, const uint32_t* __restrict__ perm) {
-    uint32_t slot_ = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot_ >= n_keys) return;
-    uint32_t key = perm[slot_];
-    uint32_t cnt = counts[key], off = offsets[key];
-    XYZZ<F> acc = XYZZ<F>::inf();
-    if (cnt > cap) {                               // left to k_bucket_heavy
-        uint32_t slot = atomicAdd(heavy, 1u);
-        heavy[1 + slot] = key;
-        buckets[key] = acc;
-        return;
-    }
-    if (cnt) {
-        if constexpr (sizeof(F) == 32) {
-            Affine<F> nxt = fetch_point(table, sorted[off]);
-            for (uint32_t k = 0; k < cnt; k++) {
-                Affine<F> cur = nxt;
-                if (k + 1 < cnt) nxt = fetch_point(table, sorted[off + k + 1]);   // overlap the gather with the add
-                acc.madd(cur);
-            }
-        } else {
-            // G2: a prefetched point costs 32 more live registers in a kernel that already spills; only the
-            // next ENTRY is read ahead, the 128-byte gather is covered by the other warps
-            uint32_t e = sorted[off];
-            for (uint32_t k = 0; k < cnt; k++) {
-                uint32_t en = k + 1 < cnt ? sorted[off + k + 1] : 0;
-                Affine<F> cur = fetch_point(table, e);
-                acc.madd(cur);
-                e = en;
-            }
-        }
-    }
-    buckets[key] = acc;
-}
-
 #ifdef OG_MSM_G1
 // G1 variant with the 128-byte accumulator in shared memory (see the G2 one below): 8 chunks of 16 bytes per thread.
 struct SmAcc1 {
@@ -442,8 +312,9 @@ struct SmAcc1 {
     }
 };
 
-template <int MINB, bool PREFETCH>
-__global__ void __launch_bounds__(128, MINB) k_bucket_acc_sm1(const Affine<Fq>* __restrict__ table, const uint32_t* __restrict__ sorted,
+// 8 CTAs of 128 threads per SM (64 registers); only the next 4-byte ENTRY is read ahead, the 64-byte gather is
+// covered by the other warps (measured against 6/7 CTAs and against a prefetched point: profiles/r1_bucket_acc_smem_sweep.md)
+__global__ void __launch_bounds__(128, 8) k_bucket_acc_sm1(const Affine<Fq>* __restrict__ table, const uint32_t* __restrict__ sorted,
                                                         const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                         uint32_t n_keys, uint32_t cap, XYZZ<Fq>* __restrict__ buckets,
                                                         uint32_t* __restrict__ heavy, const uint32_t* __restrict__ perm) {
@@ -460,18 +331,11 @@ __global__ void __launch_bounds__(128, MINB) k_bucket_acc_sm1(const Affine<Fq>* 
     }
     SmAcc1 A{sm_acc + threadIdx.x};
     bool inf = true;
-    Affine<Fq> nxt = (PREFETCH && cnt) ? fetch_point(table, sorted[off]) : Affine<Fq>::inf();
-    uint32_t e = (!PREFETCH && cnt) ? sorted[off] : 0;
+    uint32_t e = cnt ? sorted[off] : 0;
     for (uint32_t k = 0; k < cnt; k++) {
-        Affine<Fq> q;
-        if (PREFETCH) {
-            q = nxt;
-            if (k + 1 < cnt) nxt = fetch_point(table, sorted[off + k + 1]);   // overlap the gather with the add
-        } else {
-            uint32_t en = k + 1 < cnt ? sorted[off + k + 1] : 0;                // only the next entry is read ahead
-            q = fetch_point(table, e);
-            e = en;
-        }
+        uint32_t en = k + 1 < cnt ? sorted[off + k + 1] : 0;
+        Affine<Fq> q = fetch_point(table, e);
+        e = en;
         if (q.is_inf()) continue;
         if (inf) { A.st(0, q.x); A.st(1, q.y); A.st(2, Fq::one()); A.st(3, Fq::one()); inf = false; continue; }
         Fq p = q.x * A.ld(2) - A.ld(0);
@@ -515,8 +379,7 @@ struct SmAcc {
     }
 };
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_bucket_acc_sm(const Affine<Fq2>* __restrict__ table, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128, 6) k_bucket_acc_sm(const Affine<Fq2>* __restrict__ table, const uint32_t* __restrict__ sorted,
                                                        const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                        uint32_t n_keys, uint32_t cap, XYZZ<Fq2>* __restrict__ buckets,
                                                        uint32_t* __restrict__ heavy, const uint32_t* __restrict__ perm) {
@@ -642,32 +505,22 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     uint64_t avg = n_entries_max / (n_keys ? n_keys : 1);
     uint32_t cap = (uint32_t)(4 * avg < 128 ? 128 : 4 * avg);
     {
-        static const int occ = [] { const char* v = getenv(sizeof(F) == 32 ? "OG_ACC_OCC" : "OG_ACC_OCC_G2"); return v ? atoi(v) : 0; }();
+        // the long issue-bound kernel of the MSM: on the lane's low-priority stream when the prover runs chunks in flight
         const char* kn = sizeof(F) == 32 ? "k_bucket_acc_g1" : "k_bucket_acc_g2";
         unsigned grid = (n_keys + 127) / 128;
-        if constexpr (sizeof(F) == 32) {
+        cudaStream_t hi = ctx->stream;
+        if (ctx->acc_stream) { OG_CUDA(ctx, stream_handoff(ctx->acc_ev, hi, ctx->acc_stream)); ctx->stream = ctx->acc_stream; }
+        int32_t rc = [&]() -> int32_t {
 #ifdef OG_MSM_G1
-            if (occ == 17) { auto k = k_bucket_acc_sm1<7, true>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 18) { auto k = k_bucket_acc_sm1<8, true>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 26) { auto k = k_bucket_acc_sm1<6, false>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 27) { auto k = k_bucket_acc_sm1<7, false>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 0 || occ == 28) { auto k = k_bucket_acc_sm1<8, false>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 16) { auto k = k_bucket_acc_sm1<6, true>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else
+            OG_LAUNCHN(ctx, kn, k_bucket_acc_sm1, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm);
+#else
+            OG_LAUNCHN(ctx, kn, k_bucket_acc_sm, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm);
 #endif
-            if (occ == 4) { auto k = k_bucket_acc<F, 4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 6) { auto k = k_bucket_acc<F, 6>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else { auto k = k_bucket_acc<F, 5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-        } else {
-            if (occ == 2) { auto k = k_bucket_acc<F, 2>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-#ifdef OG_MSM_G2
-            else if (occ == 14) { auto k = k_bucket_acc_sm<4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 15) { auto k = k_bucket_acc_sm<5>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else if (occ == 0 || occ == 16) { auto k = k_bucket_acc_sm<6>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-#endif
-            else if (occ == 4) { auto k = k_bucket_acc<F, 4>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-            else { auto k = k_bucket_acc<F, 3>; OG_LAUNCHN(ctx, kn, k, grid, 128, 0, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, d_buckets, d_heavy, d_perm); }
-        }
+            return OG_OK;
+        }();
+        ctx->stream = hi;
+        OG_TRY(rc);
+        if (ctx->acc_stream) OG_CUDA(ctx, stream_handoff(ctx->acc_ev, ctx->acc_stream, hi));
     }
     auto k_heavy = k_bucket_heavy<F, HT>;
     OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_bucket_heavy_g1" : "k_bucket_heavy_g2", k_heavy, ctx->sm_count, HT, HT * sizeof(XYZZ<F>), d_table, d_sorted, d_offsets, d_counts, d_buckets, d_heavy);

@@ -51,66 +51,9 @@ struct PassPlan {
 
 __device__ __forceinline__ uint32_t bitrev(uint32_t x, uint32_t bits) { return __brev(x) >> (32 - bits); }
 
-__global__ void __launch_bounds__(512) k_ntt_pass(PassPlan P, const Fr* __restrict__ in, Fr* __restrict__ out,
-                                                  const Fr* __restrict__ t2, Fr n_inv) {
-    extern __shared__ __align__(32) unsigned char smem_raw[];
-    Fr* sm = reinterpret_cast<Fr*>(smem_raw);
-    const uint32_t n = 1u << P.log_n;
-    const uint32_t B0 = P.s0 - 1;                     // index bits below the ones this pass transforms
-    const uint32_t tile = 1u << (P.K + P.L);
-    const uint32_t t = blockIdx.x;
-    const uint32_t mid = t & ((1u << (B0 - P.L)) - 1), top = t >> (B0 - P.L);
-    const uint32_t base = (top << (B0 + P.K)) | (mid << P.L);
-    const Fr* src = in + (size_t)blockIdx.y * n;
-    Fr* dst = out + (size_t)blockIdx.y * n;
-    const uint32_t lmask = (1u << P.L) - 1;
-
-    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
-        uint32_t lo = e & lmask, k = e >> P.L;
-        uint32_t i = base | (k << B0) | lo;
-        Fr v;
-        if (P.first) {
-            uint32_t j = bitrev(i, P.log_n);
-            v = src[j];
-            if (P.coset && !P.inverse) v = v * t2[j];
-        } else {
-            v = src[i];
-        }
-        sm[e] = v;
-    }
-    __syncthreads();
-
-    for (uint32_t q = 1; q <= P.K; q++) {
-        const uint32_t s = P.s0 + q - 1;               // global stage: block size 2^s
-        for (uint32_t b = threadIdx.x; b < (tile >> 1); b += blockDim.x) {
-            uint32_t lo = b & lmask, kb = b >> P.L;
-            uint32_t klow = kb & ((1u << (q - 1)) - 1);
-            uint32_t k0 = ((kb >> (q - 1)) << q) | klow;
-            uint32_t e0 = (k0 << P.L) | lo, e1 = e0 + ((1u << (q - 1)) << P.L);
-            uint32_t j = (klow << B0) | (mid << P.L) | lo;          // index within the half-block, < 2^(s-1)
-            Fr w = tw2(t2, n, j << (P.log_n + 1 - s), P.inverse);   // omega_{2^s}^j = omega_{2n}^(j * 2n/2^s)
-            Fr u = sm[e0];
-            Fr v = sm[e1] * w;
-            sm[e0] = u + v;
-            sm[e1] = u - v;
-        }
-        __syncthreads();
-    }
-
-    for (uint32_t e = threadIdx.x; e < tile; e += blockDim.x) {
-        uint32_t lo = e & lmask, k = e >> P.L;
-        uint32_t i = base | (k << B0) | lo;
-        Fr v = sm[e];
-        if (P.last && P.inverse) {
-            v = v * n_inv;
-            if (P.coset) v = v * tw2(t2, n, i, true);
-        }
-        dst[i] = v;
-    }
-}
-
-// ---- version 2 of the pass kernel -----------------------------------------------------------------------
-// Same pass plan, three changes taken from the ncu capture of k_ntt_pass (profiles/): (1) two butterfly levels per
+// ---- the pass kernel ------------------------------------------------------------------------------------
+// Three things taken from the ncu capture of the first version (one level per barrier, plain array-of-structures
+// tile; profiles/r1_*; its code was removed in round 2): (1) two butterfly levels per
 // barrier with the four operands in registers (half the shared-memory round trips and barriers); (2) the 32-byte
 // elements are stored as two 16-byte chunks whose position is XOR-swizzled with bit 2 of the element index, which
 // removes the 2-way bank conflict of the plain array-of-structures layout (58 % of the wavefronts were replays);
@@ -127,10 +70,9 @@ __device__ __forceinline__ void sm_put(uint4* sm, uint32_t e, const Fr& v) {
     sm[sw_chunk(e, 1)] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-// MINB = resident CTAs per SM requested from ptxas for the 256-thread launches (registers <-> warps that can cover
-// the barriers and the gather/scatter phases of their neighbours); measured, see OG_NTT_OCC
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) k_ntt_pass2(PassPlan P, const Fr* __restrict__ in, Fr* __restrict__ out,
+// 3 resident CTAs of 256 threads per SM (80 registers): measured 35.7 -> 31.9 ms per 1024 proofs against 2 CTAs,
+// 4 CTAs (64 registers) was equal
+__global__ void __launch_bounds__(256, 3) k_ntt_pass2(PassPlan P, const Fr* __restrict__ in, Fr* __restrict__ out,
                                                    const Fr* __restrict__ t2, Fr n_inv) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     uint4* sm = reinterpret_cast<uint4*>(smem_raw);
@@ -243,6 +185,8 @@ static int32_t get_tables(og_ctx* ctx, uint32_t log_n, NttTables** out) {
     return OG_OK;
 }
 
+int32_t ntt_prepare(og_ctx* ctx, uint32_t log_n) { NttTables* T; return get_tables(ctx, log_n, &T); }
+
 void ntt_free_tables(og_ctx* ctx) {
     for (int i = 0; i < 32; i++)
         if (ctx->ntt[i]) { cudaFree(ctx->ntt[i]->d_t2); delete ctx->ntt[i]; ctx->ntt[i] = nullptr; }
@@ -282,20 +226,10 @@ int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t ba
         if (np == 1) { src = data; dst = data; }
         uint32_t tile = 1u << (p.K + p.L);
         dim3 grid((1u << log_n) / tile, batch);
-        static const int v1 = [] { const char* e = getenv("OG_NTT_V1"); return e ? atoi(e) : 0; }();
-        if (v1) {
-            uint32_t threads = tile / 2 < 32 ? 32 : (tile / 2 > 512 ? 512 : tile / 2);
-            OG_LAUNCH(ctx, k_ntt_pass, grid, threads, tile * sizeof(Fr), p, src, dst, T->d_t2, T->n_inv);
-        } else {
-            uint32_t threads = tile / 4 < 32 ? 32 : (tile / 4 > 256 ? 256 : tile / 4);
-            // the swizzle permutes chunks inside groups of 8 elements: pad tiny tiles up to one group
-            size_t smem = (tile < 8 ? 8 : tile) * sizeof(Fr);
-            static const int occ = [] { const char* e = getenv("OG_NTT_OCC"); return e ? atoi(e) : 0; }();
-            if (occ == 0 || occ == 3) { auto k = k_ntt_pass2<3>; OG_LAUNCHN(ctx, "k_ntt_pass", k, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv); }
-            else if (occ == 4) { auto k = k_ntt_pass2<4>; OG_LAUNCHN(ctx, "k_ntt_pass", k, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv); }
-            else if (occ == 2) { auto k = k_ntt_pass2<2>; OG_LAUNCHN(ctx, "k_ntt_pass", k, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv); }
-            else { auto k = k_ntt_pass2<1>; OG_LAUNCHN(ctx, "k_ntt_pass", k, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv); }
-        }
+        uint32_t threads = tile / 4 < 32 ? 32 : (tile / 4 > 256 ? 256 : tile / 4);
+        // the swizzle permutes chunks inside groups of 8 elements: pad tiny tiles up to one group
+        size_t smem = (tile < 8 ? 8 : tile) * sizeof(Fr);
+        OG_LAUNCHN(ctx, "k_ntt_pass", k_ntt_pass2, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv);
     }
     return OG_OK;
 }

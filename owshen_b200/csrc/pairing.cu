@@ -133,8 +133,8 @@ int32_t groth16_verify_host(const uint8_t* vk, uint64_t vk_len, const uint8_t* p
     if (vk_len < 12 || memcmp(vk, "OGVK", 4) != 0) return OG_E_ENCODING;
     uint32_t ver, vk_pub;
     memcpy(&ver, vk + 4, 4); memcpy(&vk_pub, vk + 8, 4);
-    if (ver != 1 || vk_pub != n_pub) return OG_E_ENCODING;
-    if (vk_len != 12 + 64 + 128 * 3 + 64ull * (n_pub + 1)) return OG_E_ENCODING;
+    if (ver != 1 || vk_pub != n_pub || n_pub > (1u << 16)) return OG_E_ENCODING;      // bound first: n_pub + 1 must not wrap
+    if (vk_len != 12 + 64 + 128 * 3 + 64ull * ((uint64_t)n_pub + 1)) return OG_E_ENCODING;
     G1Affine alpha1, A, C;
     G2Affine beta2, gamma2, delta2, B;
     const uint8_t* q = vk + 12;

@@ -30,3 +30,29 @@ class RamKvStore(KvStore):
                 self.db.pop(k, None)
             else:
                 self.db[k] = v
+
+
+class MirrorKvStore(KvStore):
+    """Write overlay over a base store, the shape of the reference's MirrorKvStore
+    (/root/reference/src/db/mirror.rs:7-50): reads fall through to the base, writes are buffered, `rollback()` returns
+    for every overwritten key the value the BASE still holds (the undo record the chain stores per block as
+    `Key::Delta`, src/blockchain/mod.rs:283-286), `buffer()` hands the pending writes over to be committed."""
+
+    def __init__(self, base: KvStore):
+        self.base = base
+        self.overwrite: Dict[bytes, Optional[bytes]] = {}
+
+    def get_raw(self, key: bytes) -> Optional[bytes]:
+        if key in self.overwrite:
+            return self.overwrite[key]
+        return self.base.get_raw(key)
+
+    def batch_put_raw(self, vals):
+        for k, v in vals:
+            self.overwrite[k] = v
+
+    def rollback(self) -> Dict[bytes, Optional[bytes]]:
+        return {k: self.base.get_raw(k) for k in self.overwrite}
+
+    def buffer(self) -> Dict[bytes, Optional[bytes]]:
+        return self.overwrite

@@ -1,6 +1,8 @@
 """World-size-2 gloo test (CPU) of the multi-GPU host logic: shard ranges, the all-gather of partial
-sums and the local combine.  The group arithmetic of each rank is done by the oracle here (there is no
-GPU and the product has no CPU path); the -m gpu test covers the same flow with the CUDA library."""
+sums and the local combine, through owshen_b200.sharded.msm_sharded itself.  The group arithmetic of each
+rank is answered by the oracle through a stand-in context (there is no GPU here and the product has no CPU
+path); tests/test_gpu_parity.py::test_msm_sharded_* run the same function with the CUDA library (device
+tensors, NCCL all-gather on the library's stream)."""
 import os
 import random
 import socket
@@ -10,7 +12,7 @@ import torch.multiprocessing as mp
 
 from oracle import bn254 as bn
 from oracle import cport
-from owshen_b200.sharded import gather_partials, shard_range, split_batch
+from owshen_b200.sharded import gather_partials, msm_sharded, shard_range, split_batch
 from tests.helpers import rand_g1
 
 
@@ -18,17 +20,28 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+class OracleCtx:
+    """What msm_sharded needs from a context without device entry points: msm_g1 / g1_sum on host bytes."""
+    def msm_g1(self, points, scalars):
+        return cport.g1_msm(points, scalars)
+
+    def g1_sum(self, points):
+        total = bytes(64)
+        for i in range(0, len(points), 64):
+            total = cport.g1_add(total, points[i:i + 64])
+        return total
+
+
 def _worker(rank, world, port, pts, sc, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
+    total = msm_sharded(OracleCtx(), pts, sc, "g1")
+    # the pieces msm_sharded is made of, checked on their own as well
     n = len(sc) // 32
     lo, hi = shard_range(n, rank, world)
-    partial = cport.g1_msm(pts[64 * lo:64 * hi], sc[32 * lo:32 * hi])
-    allp = gather_partials(partial)
-    total = bytes(64)
-    for i in range(world):
-        total = cport.g1_add(total, allp[64 * i:64 * i + 64])
+    allp = gather_partials(cport.g1_msm(pts[64 * lo:64 * hi], sc[32 * lo:32 * hi]))
+    assert OracleCtx().g1_sum(allp) == total
     q.put((rank, total))
     dist.barrier()
     dist.destroy_process_group()

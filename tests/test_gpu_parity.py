@@ -296,6 +296,173 @@ def test_groth16_prove_bit_exact_vs_oracle(ctx, keys32, monkeypatch):
     PK.close()
 
 
+def test_groth16_batch_1024_default_chunk(ctx, keys32):
+    """BASELINE config 4 at its full size and with the default chunking (what bench.py times): 1024 proofs in one call;
+    the first, the last and two seeded-random proofs are compared byte for byte with the oracle's C prover, 16 proofs
+    spread over the batch must verify against their own public inputs, and all proofs are pairwise distinct."""
+    pk, vk, cs, pkb, vkb = keys32
+    rng = random.Random(1024)
+    PK = ob.ProvingKey(ctx, pk)
+    batch = 1024
+    nul, sec, rec, sib, bits = rand_inputs(rng, batch, 32)
+    rs = cport.frs([rng.randrange(R) for _ in range(2 * batch)])
+    proofs, pub = ob.prove(PK, nul, sec, rec, sib, bits, rs)
+    PK.close()
+    assert len(proofs) == 256 * batch and len(pub) == 96 * batch
+    idx = [0, batch - 1] + sorted(rng.sample(range(1, batch - 1), 2))
+    sel = lambda b, w: b"".join(b[w * i:w * i + w] for i in idx)
+    wit = cport.withdraw_witness(sel(nul, 32), sel(sec, 32), sel(rec, 32), sel(sib, 32 * 32), [bits[i] for i in idx], 32)
+    exp = cport.Prover(cs, pkb).prove_batch(wit, sel(rs, 64))
+    for k, i in enumerate(idx):
+        assert proofs[256 * i:256 * i + 256] == exp[256 * k:256 * k + 256], i
+        assert pub[96 * i:96 * i + 96] == wit[32 * cs.n_vars * k + 32:32 * cs.n_vars * k + 128], i
+    for i in range(0, batch, 64):
+        assert ob.verify(vk, pub[96 * i:96 * i + 96], proofs[256 * i:256 * i + 256]), i
+    assert len({proofs[256 * i:256 * i + 256] for i in range(batch)}) == batch
+
+
+def test_groth16_lanes_match_serial(ctx, keys32, monkeypatch):
+    """Chunks in flight on two lanes (own scratch, own streams) must produce the bytes of the serial schedule."""
+    pk = keys32[0]
+    rng = random.Random(77)
+    PK = ob.ProvingKey(ctx, pk)
+    batch = 45
+    nul, sec, rec, sib, bits = rand_inputs(rng, batch, 32)
+    rs = cport.frs([rng.randrange(R) for _ in range(2 * batch)])
+    monkeypatch.setenv("OG_CHUNK", "1024")
+    ref = ob.prove(PK, nul, sec, rec, sib, bits, rs)
+    for chunk, lanes in ((16, 2), (7, 2), (16, 1)):
+        monkeypatch.setenv("OG_CHUNK", str(chunk)); monkeypatch.setenv("OG_LANES", str(lanes))
+        assert ob.prove(PK, nul, sec, rec, sib, bits, rs) == ref, (chunk, lanes)
+    PK.close()
+
+
+def test_merkle_append_and_rollback(ctx):
+    """og_mimc7_merkle_append against the spec tree (odd start indices, batches crossing subtree boundaries), then the
+    undo path: pop_batch / rollback restore earlier roots bit for bit; a full tree refuses more leaves."""
+    rng = random.Random(41)
+    depth = 9
+    t = ob.MerkleTree(ctx, depth); ref = mimc7.MerkleTree(depth)
+    roots, sizes, vals = [t.root()], [0], []
+    for n in (1, 2, 5, 1, 64, 3, 100):
+        batch = [rng.randrange(R) for _ in range(n)]
+        t.insert_batch(batch); vals += batch
+        for v in batch:
+            ref.insert(v)
+        assert int.from_bytes(t.root(), "little") == ref.root(), n
+        roots.append(t.root()); sizes.append(t.n_leaves)
+    for i in (0, 7, 8, 72, 175):
+        sib, bits = t.path(i)
+        assert sib == b"".join(bn.fr_to_bytes(x) for x in ref.path(i)[0])
+        assert ctx.merkle_paths(bn.fr_to_bytes(vals[i]), sib, [bits], depth)[-32:] == t.root()
+    assert t.pop_batch() == 100 and t.root() == roots[-2]
+    t.rollback(sizes[3])
+    assert t.root() == roots[3] and t.n_leaves == sizes[3]
+    t.rollback(5)                                            # inside the third batch
+    r5 = mimc7.MerkleTree(depth)
+    for v in vals[:5]:
+        r5.insert(v)
+    assert int.from_bytes(t.root(), "little") == r5.root()
+    t.rollback(0)
+    assert t.root() == roots[0]
+    small = ob.MerkleTree(ctx, 2)
+    small.insert_batch([1, 2, 3])
+    with pytest.raises(OverflowError):
+        small.insert_batch([4, 5])
+    small.insert(4)
+    with pytest.raises(OverflowError):
+        small.insert(5)
+    with pytest.raises(ValueError):
+        ctx.merkle_append(2, 3, bytes(64), bytes(64), bytes(64))      # 2 leaves at index 3 of a 4-leaf tree
+
+
+def _nccl_world1():
+    import socket
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    return dist
+
+
+def test_msm_sharded_world1_vs_oracle_and_single_gpu(ctx):
+    """BASELINE config 5 through the product function owshen_b200.sharded.msm_sharded (NCCL process group of this box's
+    one visible rank): 2^16 G1 / 2^13 G2 against the oracle's CPU MSM, 2^20 G1 against the single-GPU entry point, and
+    the device-tensor variant against the host-buffer one."""
+    import torch
+    from owshen_b200.sharded import msm_sharded, msm_sharded_dev
+    dist = _nccl_world1()
+    try:
+        rng = random.Random(55)
+        n = 1 << 16
+        pts, sc = rand_g1(rng, n), rand_fr_bytes(rng, n)
+        got = msm_sharded(ctx, pts, sc, "g1")
+        assert got == cport.g1_msm(pts, sc)
+        n2 = 1 << 13
+        pts2, sc2 = rand_g2(rng, n2), rand_fr_bytes(rng, n2)
+        assert msm_sharded(ctx, pts2, sc2, "g2") == cport.g2_msm(pts2, sc2)
+        dev = torch.device("cuda", ctx.device)
+        d_p = torch.frombuffer(bytearray(pts), dtype=torch.uint8).to(dev)
+        d_s = torch.frombuffer(bytearray(sc), dtype=torch.uint8).to(dev)
+        torch.cuda.synchronize()
+        res = msm_sharded_dev(ctx, d_p, d_s, "g1")
+        ctx.sync()
+        assert bytes(res.cpu().numpy().tobytes()) == got
+        n = 1 << 20
+        ks = rand_fr_bytes(rng, n)
+        big = ctx.g1_generator_mul(ks)
+        sc = rand_fr_bytes(rng, n)
+        assert msm_sharded(ctx, big, sc, "g1") == ctx.msm_g1(big, sc)
+        assert msm_sharded(ctx, b"", b"", "g1") == bytes(64)
+        with pytest.raises(ValueError):
+            msm_sharded(ctx, pts[:64], sc[:64], "g1")
+    finally:
+        dist.destroy_process_group()
+
+
+def _sharded_worker(rank, world, port, pts, sc, pts2, sc2, q):
+    import torch
+    import torch.distributed as dist
+    from owshen_b200.sharded import msm_sharded
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    c = ob.Context(rank)
+    try:
+        q.put((rank, msm_sharded(c, pts, sc, "g1"), msm_sharded(c, pts2, sc2, "g2")))
+        dist.barrier()
+    finally:
+        c.close()
+        dist.destroy_process_group()
+
+
+def test_msm_sharded_two_gpus(ctx):
+    """The same function over a real NCCL all-gather: two ranks, two GPUs, results equal the single-GPU MSM and the oracle."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = random.Random(56)
+    n, n2 = 50001, 3001
+    pts, sc = rand_g1(rng, n), rand_fr_bytes(rng, n)
+    pts2, sc2 = rand_g2(rng, n2), rand_fr_bytes(rng, n2)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_sharded_worker, args=(r, 2, port, pts, sc, pts2, sc2, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    e1, e2 = cport.g1_msm(pts, sc), cport.g2_msm(pts2, sc2)
+    assert e1 == ctx.msm_g1(pts, sc) and e2 == ctx.msm_g2(pts2, sc2)
+    for _, g1, g2 in got:
+        assert g1 == e1 and g2 == e2
+
+
 def test_pk_blob_rejects_garbage(ctx, keys32):
     pk = keys32[0]
     with pytest.raises(ob.OwshenB200Error):

@@ -1,6 +1,7 @@
-"""Host logic of owshen_b200.api.MerkleTree (sparse tree bookkeeping, KvStore persistence, path extraction) on the CPU:
-the tree only asks its context for batched two-to-one hashes, so a stand-in context that answers them from the oracle
-exercises everything but the kernel (the kernel's own parity is tests/test_gpu_parity.py)."""
+"""Host logic of owshen_b200.api.MerkleTree (sparse tree bookkeeping, KvStore persistence, undo records, path
+extraction) on the CPU: the tree only asks its context for two-to-one hashes (the empty-subtree roots) and for the
+nodes touched by an append, so a stand-in context that answers both from the oracle exercises everything but the
+kernels (their own parity is tests/test_gpu_parity.py)."""
 import random
 
 import pytest
@@ -25,6 +26,22 @@ class OracleHashCtx:
             out.append(mimc7.hash2(a, b).to_bytes(32, "little"))
         return b"".join(out)
 
+    def merkle_append(self, depth, start, leaves, left_boundary, zeros):
+        """Restates og_mimc7_merkle_append (include/owshen_b200.h) with the oracle hash."""
+        self.append_calls = getattr(self, "append_calls", 0) + 1
+        cur = [int.from_bytes(leaves[i:i + 32], "little") for i in range(0, len(leaves), 32)]
+        c0, out = start, []
+        for l in range(depth):
+            lb = int.from_bytes(left_boundary[32 * l:32 * l + 32], "little")
+            z = int.from_bytes(zeros[32 * l:32 * l + 32], "little")
+            def child(i):
+                return lb if i < c0 else (cur[i - c0] if i < c0 + len(cur) else z)
+            p0, p1 = c0 >> 1, (c0 + len(cur) - 1) >> 1
+            nxt = [mimc7.hash2(child(2 * p), child(2 * p + 1)) for p in range(p0, p1 + 1)]
+            out += nxt
+            cur, c0 = nxt, p0
+        return b"".join(x.to_bytes(32, "little") for x in out)
+
 
 def fr(x):
     return x.to_bytes(32, "little")
@@ -39,9 +56,9 @@ def test_insert_root_path_match_the_spec_tree():
     leaves = [rng.randrange(bn.R) for _ in range(11)]
     idx = t.insert_batch([fr(x) for x in leaves[:7]])
     assert idx == list(range(7))
-    before = ctx.calls
+    before = ctx.append_calls
     assert t.insert(fr(leaves[7])) == 7
-    assert ctx.calls - before == 6                          # one batched hash call per level
+    assert ctx.append_calls - before == 1                   # one library call per insert, whatever the depth
     t.insert_batch(leaves[8:])                              # integers are accepted too
     for x in leaves:
         ref.insert(x)
@@ -75,3 +92,74 @@ def test_reopen_over_the_same_store():
         api.MerkleTree(ctx, 4, store=store)
     other = api.MerkleTree(ctx, 5, store=store, prefix=b"other/")    # a second tree in the same store
     assert other.n_leaves == 0 and other.root() != t2.root()
+
+
+def test_capacity_is_enforced():
+    ctx = OracleHashCtx()
+    t = api.MerkleTree(ctx, 3)
+    t.insert_batch([fr(i + 1) for i in range(6)])
+    root, n = t.root(), t.n_leaves
+    with pytest.raises(OverflowError):
+        t.insert_batch([fr(7), fr(8), fr(9)])               # 6 + 3 > 2^3: nothing may be written
+    assert t.root() == root and t.n_leaves == n
+    t.insert_batch([fr(7), fr(8)])                          # exactly full is fine
+    assert t.n_leaves == 8
+    sib, bits = t.path(7)
+    node = 8
+    for lvl in range(3):
+        s = int.from_bytes(sib[32 * lvl:32 * lvl + 32], "little")
+        node = mimc7.hash2(s, node) if (bits >> lvl) & 1 else mimc7.hash2(node, s)
+    assert fr(node) == t.root()
+    with pytest.raises(OverflowError):
+        t.insert(fr(9))
+
+
+def test_pop_batch_and_rollback_restore_earlier_roots():
+    """Undo semantics of the reference's pop_block (src/blockchain/mod.rs:291-315): applying the stored delta restores
+    every overwritten key, and the delta itself is deleted."""
+    rng = random.Random(9)
+    ctx = OracleHashCtx()
+    store = RamKvStore()
+    t = api.MerkleTree(ctx, 5, store=store)
+    roots, sizes = [t.root()], [0]
+    snapshot0 = dict(store.db)
+    for n in (3, 1, 6, 2):
+        t.insert_batch([fr(rng.randrange(bn.R)) for _ in range(n)])
+        roots.append(t.root()); sizes.append(t.n_leaves)
+    assert t.n_batches == 4
+    assert t.pop_batch() == 2 and t.root() == roots[3] and t.n_leaves == sizes[3] and t.n_batches == 3
+    # a reopened tree sees the popped state; re-inserting other leaves gives a different root, popping them restores it
+    t2 = api.MerkleTree(ctx, 5, store=store)
+    t2.insert_batch([fr(1), fr(2)])
+    assert t2.root() != roots[4]
+    t2.pop_batch()
+    assert t2.root() == roots[3]
+    # rollback to a batch boundary and into the middle of a batch
+    t.rollback(sizes[2])
+    assert t.root() == roots[2] and t.n_leaves == 4
+    ref = mimc7.MerkleTree(5)
+    leaves = [int.from_bytes(store.get_raw(t._key(0, i)), "little") for i in range(4)]
+    for x in leaves[:2]:
+        ref.insert(x)
+    t.rollback(2)                                            # inside the first batch of 3
+    assert t.n_leaves == 2 and t.root() == fr(ref.root())
+    assert t.path(1)[0] == b"".join(fr(x) for x in ref.path(1)[0])
+    t.rollback(0)
+    assert t.root() == roots[0] and t.n_leaves == 0 and t.n_batches == 0
+    live = {k: v for k, v in store.db.items() if k != b"mt/depth"}
+    assert live == {k: v for k, v in snapshot0.items() if k != b"mt/depth"}      # nothing left behind, deltas included
+    assert t.pop_batch() == 0
+    with pytest.raises(ValueError):
+        t.rollback(1)
+
+
+def test_mirror_kvstore_matches_the_reference_shape():
+    from owshen_b200.kvstore import MirrorKvStore
+    base = RamKvStore()
+    base.batch_put_raw([(b"a", b"1"), (b"b", b"2")])
+    m = MirrorKvStore(base)
+    m.batch_put_raw([(b"a", b"9"), (b"c", b"3"), (b"b", None)])
+    assert m.get_raw(b"a") == b"9" and m.get_raw(b"b") is None and m.get_raw(b"c") == b"3" and base.get_raw(b"a") == b"1"
+    assert m.rollback() == {b"a": b"1", b"b": b"2", b"c": None}           # mirror.rs:19-27
+    base.batch_put_raw(m.buffer().items())
+    assert base.db == {b"a": b"9", b"c": b"3"}
