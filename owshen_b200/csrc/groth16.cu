@@ -331,8 +331,12 @@ struct ChunkBufs {
     uint32_t *counts, *offsets, *cursor, *sorted, *heavy;
     G1XYZZ *bk1, *lvl1, *totA, *totC;
     G2XYZZ *bk2, *lvl2, *totB;
+    void *aff1, *aff2;                    // batched-affine scratch (nullptr = XYZZ accumulation): G1 MSMs / G2 MSM
     uint32_t w_stride, bsc_stride, csc_stride;
 };
+
+// OG_AFFINE: bit 0 = batched-affine accumulation for the G1 MSMs of the prover, bit 1 = for the G2 MSM
+static uint32_t affine_mode() { return env_u32("OG_AFFINE", 0); }
 
 // W, rs_m and the per-proof totals cover the whole batch; everything else is per chunk of B proofs and per lane
 static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_t B, int lane, ChunkBufs& b) {
@@ -357,6 +361,16 @@ static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_
     b.totA = (G1XYZZ*)ctx->slot(S_PR_SUMS, (sizeof(G1XYZZ) * 2 + sizeof(G2XYZZ)) * (size_t)batch);
     if (!b.W || !b.rs_m || !b.abc || !b.bsc || !b.sorted || !b.counts || !b.offsets || !b.cursor || !b.heavy || !b.bk2 || !b.lvl2 || !b.totA)
         return OG_E_NOMEM;
+    b.aff1 = b.aff2 = nullptr;
+    if (affine_mode()) {
+        size_t need = 0;
+        if (affine_mode() & 1) need = msm_aff_scratch_bytes_g1(n_keys);
+        if ((affine_mode() & 2) && msm_aff_scratch_bytes_g2((size_t)B * pk->nb[1]) > need) need = msm_aff_scratch_bytes_g2((size_t)B * pk->nb[1]);
+        void* a = ctx->slot(S(S_PR_AFF, S_L1_AFF), need);
+        if (!a) return OG_E_NOMEM;
+        if (affine_mode() & 1) b.aff1 = a;
+        if (affine_mode() & 2) b.aff2 = a;
+    }
     b.ntt_tmp = b.abc + (size_t)B * 3 * m;
     b.csc = b.bsc + (size_t)B * b.bsc_stride;
     b.bk1 = reinterpret_cast<G1XYZZ*>(b.bk2);       // the G1 and G2 MSMs of a chunk run one after another
@@ -376,7 +390,7 @@ static int32_t run_msm_g1(og_ctx* ctx, const og_pk* pk, int which, ChunkBufs& b,
     plan.montgomery = 1;
     uint32_t n_keys = B * pk->nb[which];
     OG_TRY(msm_sort_digits(ctx, plan, n_keys, b.counts, b.offsets, b.cursor, b.sorted));
-    return msm_buckets_g1(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb[which], (uint64_t)B * n_pts * pk->n_windows[which], b.bk1, b.lvl1, b.heavy, b.cursor, totals);
+    return msm_buckets_g1(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb[which], (uint64_t)B * n_pts * pk->n_windows[which], b.bk1, b.lvl1, b.heavy, b.cursor, totals, b.aff1);
 }
 static int32_t run_msm_g2(og_ctx* ctx, const og_pk* pk, int which, ChunkBufs& b, uint32_t B, const G2Affine* table, uint32_t n_pts,
                           const Fr* scalars, uint32_t stride, G2XYZZ* totals) {
@@ -388,7 +402,7 @@ static int32_t run_msm_g2(og_ctx* ctx, const og_pk* pk, int which, ChunkBufs& b,
     plan.montgomery = 1;
     uint32_t n_keys = B * pk->nb[which];
     OG_TRY(msm_sort_digits(ctx, plan, n_keys, b.counts, b.offsets, b.cursor, b.sorted));
-    return msm_buckets_g2(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb[which], (uint64_t)B * n_pts * pk->n_windows[which], b.bk2, b.lvl2, b.heavy, b.cursor, totals);
+    return msm_buckets_g2(ctx, table, b.sorted, b.offsets, b.counts, B, pk->nb[which], (uint64_t)B * n_pts * pk->n_windows[which], b.bk2, b.lvl2, b.heavy, b.cursor, totals, b.aff2);
 }
 
 // where a chunk's witness rows come from
