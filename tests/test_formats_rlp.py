@@ -63,3 +63,21 @@ def test_shielded_withdraw_roundtrip():
             F.shielded_withdraw_from_rlp(broken)
     with pytest.raises(ValueError):
         F.shielded_withdraw_to_rlp(proof[:-1], pub)
+
+
+def test_shielded_withdraw_rlp_kat_shared_with_rust():
+    """The known answer bindings/rust/route.rs asserts in its own (uncompiled) unit test: both sides must produce these
+    bytes, so the constants are read out of the Rust source rather than repeated here."""
+    import hashlib
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "bindings", "rust", "route.rs")).read()
+    kat_len = int(re.search(r"KAT_LEN: usize = (\d+);", src).group(1))
+    prefix = re.search(r'KAT_PREFIX_HEX: &str = "([0-9a-f]+)";', src).group(1)
+    digest = re.search(r'KAT_SHA256_HEX: &str = "([0-9a-f]+)";', src).group(1)
+    kind = re.search(r'SHIELDED_WITHDRAW_KIND: &str = "([^"]+)";', src).group(1)
+    assert kind == F.SHIELDED_WITHDRAW_KIND
+    proof = bytes(range(256))
+    pub = bytes((7 * i + 3) % 256 for i in range(96))
+    msg = F.shielded_withdraw_to_rlp(proof, pub)
+    assert len(msg) == kat_len and msg[:24].hex() == prefix and hashlib.sha256(msg).hexdigest() == digest
+    assert F.shielded_withdraw_from_rlp(msg) == (proof, pub)

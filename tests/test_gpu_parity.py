@@ -425,6 +425,21 @@ def test_batched_affine_accumulation_matches_xyzz(ctx, keys32, monkeypatch):
     assert ctx.msm_g1(big, bsc) == cport.g1_msm(big, bsc)
 
 
+def test_external_known_answers(ctx):
+    """The CUDA library against published vectors it did not produce (tests/golden/external_vectors.json): EIP-196 point
+    addition / scalar multiplication through og_g1_sum / og_msm_g1 / the fixed-base generator path."""
+    ext = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "external_vectors.json")))["eip196"]
+    pt = lambda xy: bn.g1_to_bytes((int(xy[0], 16), int(xy[1], 16)))
+    add = ext["add_chfast1"]
+    assert ctx.g1_sum(pt(add["a"]) + pt(add["b"])) == pt(add["sum"])
+    mul = ext["mul_chfast1"]
+    assert ctx.msm_g1(pt(mul["p"]), cport.frs([int(mul["k"], 16)])) == pt(mul["product"])
+    two = pt([ext["g1_generator_doubled"]["x"], ext["g1_generator_doubled"]["y"]])
+    assert ctx.g1_generator_mul(cport.frs([2])) == two
+    assert ctx.g1_sum(bn.g1_to_bytes(bn.G1_GEN) * 2) == two
+    assert ctx.msm_g1(pt(add["a"]) + pt(add["b"]), cport.frs([1, 1])) == pt(add["sum"])
+
+
 def _nccl_world1():
     import socket
     import torch.distributed as dist
