@@ -11,7 +11,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libowshen_b200.so")
+# OWSHEN_B200_LIB: an alternative build of the same library (A/B experiments of compile-time variants)
+_LIB_PATH = os.environ.get("OWSHEN_B200_LIB") or os.path.join(_HERE, "libowshen_b200.so")
 _lib = None
 
 FR_MODULUS = 21888242871839275222246405745257275088548364400416034343698204186575808495617
@@ -59,6 +60,7 @@ _SIGS = {
     "og_mimc7_merkle_build": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_mimc7_merkle_append": (C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "og_bjj_verify_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]),
+    "og_bjj_sign_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "og_msm_g1": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_msm_g2": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "og_msm_g1_dev": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
@@ -290,6 +292,18 @@ class Context:
         out = C.create_string_buffer(n)
         _check(lib().og_bjj_verify_batch(self._h, pk_x, pk_is_odd, messages, signatures, n, hash_kind, out), self)
         return out.raw
+
+    def bjj_sign_batch(self, secret_keys: bytes, randomness: bytes, messages: bytes, hash_kind: int = 0):
+        """BabyJubJub key derivation + signing, one key per 32 bytes: -> (pk_x, pk_is_odd, signatures, status) with
+        status 1 = signed, 2 = the reference's sign() would return Err("Invalid repr")."""
+        _need(len(secret_keys) % 32 == 0 and len(randomness) == len(secret_keys) and len(messages) == len(secret_keys),
+              "bjj_sign_batch: keys, randomness and messages must be equally long multiples of 32 bytes")
+        _need(hash_kind in (0, 1), "bjj_sign_batch: hash_kind must be 0 or 1")
+        n = len(secret_keys) // 32
+        px, odd = C.create_string_buffer(32 * n), C.create_string_buffer(n)
+        sg, st = C.create_string_buffer(96 * n), C.create_string_buffer(n)
+        _check(lib().og_bjj_sign_batch(self._h, secret_keys, randomness, messages, n, hash_kind, px, odd, sg, st), self)
+        return px.raw, odd.raw[:n], sg.raw, st.raw[:n]
 
     def msm_g1(self, points: bytes, scalars: bytes) -> bytes:
         _need(len(scalars) % 32 == 0, "msm_g1: scalars must be a multiple of 32 bytes")

@@ -117,4 +117,73 @@ OG_HD uint8_t bjj_verify_one(const Fr& x, bool pk_odd, const Fr& msg, const Fr& 
     return eq ? 1 : 0;
 }
 
+// ---- signing and key derivation (mod.rs:206-237) -----------------------------------------------------------------
+// ORDER = 8 * l (mod.rs:185-188), little-endian 32-bit limbs
+OG_HD uint32_t bjj_order_limb(int i) {
+    constexpr uint32_t o[8] = {0xc9093788u, 0x3b94bee1u, 0xc9077053u, 0x59f76dc1u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+    return o[i];
+}
+
+// out = (r + h * a) mod ORDER on canonical integers (the reference does this in BigUint, mod.rs:224-228)
+OG_BJJ_FN void bjj_s_mod_order(uint32_t* out, const uint32_t* r, const uint32_t* h, const uint32_t* a) {
+    uint32_t t[17];
+    for (int i = 0; i < 17; i++) t[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 8; j++) {
+            uint64_t v = (uint64_t)h[i] * a[j] + t[i + j] + carry;
+            t[i + j] = (uint32_t)v; carry = v >> 32;
+        }
+        t[i + 8] = (uint32_t)carry;
+    }
+    uint64_t c = 0;
+    for (int i = 0; i < 17; i++) { uint64_t v = (uint64_t)t[i] + (i < 8 ? r[i] : 0) + c; t[i] = (uint32_t)v; c = v >> 32; }
+    // binary long division: rem < ORDER < 2^254 throughout, so rem * 2 + bit fits 8 limbs
+    uint32_t rem[8];
+    for (int i = 0; i < 8; i++) rem[i] = 0;
+    for (int bit = 17 * 32 - 1; bit >= 0; bit--) {
+        uint32_t in = (t[bit >> 5] >> (bit & 31)) & 1;
+        for (int i = 7; i > 0; i--) rem[i] = (rem[i] << 1) | (rem[i - 1] >> 31);
+        rem[0] = (rem[0] << 1) | in;
+        uint32_t d[8];
+        uint64_t borrow = 0;
+        for (int i = 0; i < 8; i++) { uint64_t v = (uint64_t)rem[i] - bjj_order_limb(i) - borrow; d[i] = (uint32_t)v; borrow = (v >> 63) & 1; }
+        if (!borrow) for (int i = 0; i < 8; i++) rem[i] = d[i];
+    }
+    for (int i = 0; i < 8; i++) out[i] = rem[i];
+}
+
+// the reference's to_affine (mod.rs:165-171): the empty accumulator is the affine neutral element (0, 1)
+OG_BJJ_FN void bjj_to_affine(Fr* x, Fr* y, const BjjPoint* p) {
+    if (p->z.is_zero()) { *x = Fr::zero(); *y = Fr::one(); return; }
+    Fr zi = p->z.inv();
+    *x = p->x * zi; *y = p->y * zi;
+}
+
+// PrivateKey::to_pub + sign (mod.rs:207-237).  status 1: pk and signature written; 2: the reference returns
+// Err("Invalid repr") because s >= r cannot be represented as an Fp (ORDER > r: the wart SURVEY.md 8a notes).
+template <class HashFn2, class HashFn5>
+OG_HD uint8_t bjj_sign_one(const Fr& sk, const Fr& randomness, const Fr& msg, const Fr& base_x, const Fr& base_y, HashFn2 hash2,
+                           HashFn5 hash5, Fr* pk_x, bool* pk_odd, Fr* sig_rx, Fr* sig_ry, Fr* sig_s) {
+    const Fr A = bjj_a(), D = bjj_d(), one = Fr::one();
+    BjjPoint base{base_x, base_y, one}, acc;
+    Fr px, py, rx, ry;
+    bjj_mul(&acc, &base, &sk, &A, &D);               // to_pub: BASE * sk, compressed (x, parity of y); decompressing gives y back
+    bjj_to_affine(&px, &py, &acc);
+    *pk_x = px; *pk_odd = fr_is_odd(py);
+    Fr in2[2] = {randomness, msg};
+    Fr r = hash2(in2);                                 // r = H(b, M)
+    bjj_mul(&acc, &base, &r, &A, &D);                // R = r B
+    bjj_to_affine(&rx, &ry, &acc);
+    Fr in5[5] = {rx, ry, px, py, msg};
+    Fr h = hash5(in5);                                 // h = H(R, A, M)
+    uint32_t rc[8], hc[8], ac[8], sc[8];
+    r.to_canonical(rc); h.to_canonical(hc); sk.to_canonical(ac);
+    bjj_s_mod_order(sc, rc, hc, ac);                   // s = (r + h a) mod ORDER
+    *sig_rx = rx; *sig_ry = ry;
+    if (!Fr::canonical_lt_mod(sc)) { *sig_s = Fr::zero(); return 2; }
+    *sig_s = Fr::from_canonical(sc);
+    return 1;
+}
+
 }  // namespace og

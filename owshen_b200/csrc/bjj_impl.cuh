@@ -17,11 +17,12 @@ namespace og {
 __constant__ uint32_t BJJ_BASE_X[8] = {0xbb957051u, 0x2893f3f6u, 0x0534e0b6u, 0x2ab8d801u, 0x9d6277c1u, 0x4eacb2e0u, 0xd63e739bu, 0x0bb77a6au};   // mod.rs:177-183
 __constant__ uint32_t BJJ_BASE_Y[8] = {0x872d7d8bu, 0x4b3c257au, 0xb9e13377u, 0xfce0051fu, 0xd16bf9edu, 0x25572e1cu, 0xf7a0b249u, 0x25797203u};
 
-static __device__ __noinline__ Fr mimc7_multi_hash5(const Fr* in) {     // MultiMiMC7(in[0..5), key 0)
+static __device__ __noinline__ Fr mimc7_multi_hash_n(const Fr* in, int n) {     // MultiMiMC7(in[0..n), key 0)
     Fr r = Fr::zero();
-    for (int k = 0; k < 5; k++) r = r + in[k] + mimc7_hash<false>(in[k], r, nullptr);
+    for (int k = 0; k < n; k++) r = r + in[k] + mimc7_hash<false>(in[k], r, nullptr);
     return r;
 }
+static __device__ __forceinline__ Fr mimc7_multi_hash5(const Fr* in) { return mimc7_multi_hash_n(in, 5); }
 
 // out[i]: 1 = verifies, 0 = does not, 2 = the reference would return Err (public key does not decompress)
 __global__ void __launch_bounds__(64) k_bjj_verify(const uint8_t* __restrict__ pk_x, const uint8_t* __restrict__ pk_odd,
@@ -41,6 +42,36 @@ __global__ void __launch_bounds__(64) k_bjj_verify(const uint8_t* __restrict__ p
         if (hash_kind == 0) return in[0] * in[1] * in[2] * in[3] * in[4];     // placeholder product, mod.rs:202-204
         return mimc7_multi_hash5(in);
     });
+}
+
+// batch of PrivateKey::to_pub + PrivateKey::sign (mod.rs:207-237): one thread per key
+__global__ void __launch_bounds__(64) k_bjj_sign(const uint8_t* __restrict__ sks, const uint8_t* __restrict__ rnds, const uint8_t* __restrict__ msgs,
+                                                 uint32_t n, int hash_kind, uint8_t* __restrict__ pk_x, uint8_t* __restrict__ pk_odd,
+                                                 uint8_t* __restrict__ sigs, uint8_t* __restrict__ status, int* flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr sk = load_canonical<Fr>(sks + 32ull * i, flag), rnd = load_canonical<Fr>(rnds + 32ull * i, flag), msg = load_canonical<Fr>(msgs + 32ull * i, flag);
+    uint32_t bxc[8], byc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { bxc[k] = BJJ_BASE_X[k]; byc[k] = BJJ_BASE_Y[k]; }
+    const Fr bx = Fr::from_canonical(bxc), by = Fr::from_canonical(byc);
+    Fr px, rx, ry, s;
+    bool odd;
+    uint8_t st = bjj_sign_one(sk, rnd, msg, bx, by,
+        [hash_kind](const Fr* in) { return hash_kind == 0 ? in[0] * in[1] : mimc7_multi_hash_n(in, 2); },
+        [hash_kind](const Fr* in) { return hash_kind == 0 ? in[0] * in[1] * in[2] * in[3] * in[4] : mimc7_multi_hash_n(in, 5); },
+        &px, &odd, &rx, &ry, &s);
+    store_canonical(pk_x + 32ull * i, px);
+    pk_odd[i] = odd ? 1 : 0;
+    store_canonical(sigs + 96ull * i, rx); store_canonical(sigs + 96ull * i + 32, ry); store_canonical(sigs + 96ull * i + 64, s);
+    status[i] = st;
+}
+
+int32_t bjj_sign_dev(og_ctx* ctx, const uint8_t* d_sk, const uint8_t* d_rnd, const uint8_t* d_msgs, uint32_t n, int hash_kind,
+                     uint8_t* d_pk_x, uint8_t* d_pk_odd, uint8_t* d_sigs, uint8_t* d_status) {
+    if (n == 0) return OG_OK;
+    OG_LAUNCH(ctx, k_bjj_sign, (n + 63) / 64, 64, 0, d_sk, d_rnd, d_msgs, n, hash_kind, d_pk_x, d_pk_odd, d_sigs, d_status, ctx->d_flag);
+    return OG_OK;
 }
 
 int32_t bjj_verify_dev(og_ctx* ctx, const uint8_t* d_pk_x, const uint8_t* d_pk_odd, const uint8_t* d_msgs, const uint8_t* d_sigs,

@@ -2,6 +2,7 @@
 // Host-pointer entry points stage their buffers in persistent device slots (H2D/D2H on the ctx
 // stream, truly asynchronous when the caller's memory is pinned) and return after the result has
 // landed; `_dev` entry points only enqueue.  No entry point has a CPU implementation.
+#include <stdlib.h>
 #include "common.cuh"
 #include "groth16.cuh"
 #include "mimc.cuh"
@@ -110,6 +111,7 @@ int32_t og_init(int32_t device, og_ctx** out) {
     {
         int least = 0, greatest = 0;
         cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        { const char* v = getenv("OG_LANE_PRIO"); if (v && atoi(v) == 0) least = greatest = 0; }   // A/B: lanes without stream priorities
         bool ok = cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&ctx->acc_ev, cudaEventDisableTiming) == cudaSuccess;
         for (int l = 0; ok && l < MAX_LANES; l++)
@@ -599,6 +601,26 @@ int32_t og_bjj_verify_batch(og_ctx* ctx, const uint8_t* pk_x, const uint8_t* pk_
     H2D(ctx, dx, pk_x, 32ull * n); H2D(ctx, dodd, pk_is_odd, n); H2D(ctx, dm, messages, 32ull * n); H2D(ctx, dsg, signatures, 96ull * n);
     OG_TRY(bjj_verify_dev(ctx, dx, dodd, dm, dsg, n, hash_kind, dout));
     D2H(ctx, out_status, dout, n);
+    return check_flag(ctx);
+}
+
+int32_t og_bjj_sign_batch(og_ctx* ctx, const uint8_t* secret_keys, const uint8_t* randomness, const uint8_t* messages, uint32_t n,
+                          int32_t hash_kind, uint8_t* out_pk_x, uint8_t* out_pk_is_odd, uint8_t* out_signatures, uint8_t* out_status) {
+    OG_ENTER(ctx);
+    if (!ctx || !secret_keys || !randomness || !messages || !out_pk_x || !out_pk_is_odd || !out_signatures || !out_status || hash_kind < 0 || hash_kind > 1)
+        return OG_E_INVALID;
+    if (n == 0) return OG_OK;
+    OG_SLOT(ctx, dsk, uint8_t, S_IO_A, 32ull * n);
+    OG_SLOT(ctx, drn, uint8_t, S_IO_B, 32ull * n);
+    OG_SLOT(ctx, dm, uint8_t, S_IO_C, 32ull * n);
+    OG_SLOT(ctx, dpx, uint8_t, S_IO_D, 32ull * n);
+    OG_SLOT(ctx, dodd, uint8_t, S_IO_E, n);
+    OG_SLOT(ctx, dsg, uint8_t, S_IO_F, 96ull * n);
+    OG_SLOT(ctx, dst, uint8_t, S_IO_G, n);
+    OG_TRY(clear_flag(ctx));
+    H2D(ctx, dsk, secret_keys, 32ull * n); H2D(ctx, drn, randomness, 32ull * n); H2D(ctx, dm, messages, 32ull * n);
+    OG_TRY(bjj_sign_dev(ctx, dsk, drn, dm, n, hash_kind, dpx, dodd, dsg, dst));
+    D2H(ctx, out_pk_x, dpx, 32ull * n); D2H(ctx, out_pk_is_odd, dodd, n); D2H(ctx, out_signatures, dsg, 96ull * n); D2H(ctx, out_status, dst, n);
     return check_flag(ctx);
 }
 

@@ -335,8 +335,13 @@ struct ChunkBufs {
     uint32_t w_stride, bsc_stride, csc_stride;
 };
 
-// OG_AFFINE: bit 0 = batched-affine accumulation for the G1 MSMs of the prover, bit 1 = for the G2 MSM
+// experiment builds only (-DOG_EXPERIMENT_AFFINE, csrc/experiments/bucket_affine.cuh): OG_AFFINE bit 0 = batched-affine
+// accumulation for the G1 MSMs of the prover, bit 1 = for the G2 MSM.  The shipped library has no such path.
+#ifdef OG_EXPERIMENT_AFFINE
 static uint32_t affine_mode() { return env_u32("OG_AFFINE", 0); }
+#else
+static uint32_t affine_mode() { return 0; }
+#endif
 
 // W, rs_m and the per-proof totals cover the whole batch; everything else is per chunk of B proofs and per lane
 static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_t B, int lane, ChunkBufs& b) {
@@ -355,7 +360,7 @@ static int32_t alloc_chunk(og_ctx* ctx, const og_pk* pk, uint32_t batch, uint32_
     b.counts = (uint32_t*)ctx->slot(S(S_PR_COUNTS, S_L1_COUNTS), 4 * n_keys);
     b.offsets = (uint32_t*)ctx->slot(S(S_PR_OFFSETS, S_L1_OFFSETS), 4 * (n_keys + 1));
     b.cursor = (uint32_t*)ctx->slot(S(S_PR_CURSOR, S_L1_CURSOR), 4 * n_keys);
-    b.heavy = (uint32_t*)ctx->slot(S(S_PR_HEAVY, S_L1_HEAVY), 4 * (n_keys + 1));
+    b.heavy = (uint32_t*)ctx->slot(S(S_PR_HEAVY, S_L1_HEAVY), 4 * (2 * n_keys + 4));
     b.bk2 = (G2XYZZ*)ctx->slot(S(S_PR_BUCKETS, S_L1_BUCKETS), sizeof(G2XYZZ) * n_keys);
     b.lvl2 = (G2XYZZ*)ctx->slot(S(S_PR_SEG, S_L1_SEG), sizeof(G2XYZZ) * msm_lvl_elems(B, pk->max_nb));
     b.totA = (G1XYZZ*)ctx->slot(S_PR_SUMS, (sizeof(G1XYZZ) * 2 + sizeof(G2XYZZ)) * (size_t)batch);

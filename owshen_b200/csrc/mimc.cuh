@@ -38,4 +38,8 @@ int32_t withdraw_witness_strided_dev(og_ctx* ctx, const WithdrawLayout& L, uint3
 int32_t bjj_verify_dev(og_ctx* ctx, const uint8_t* d_pk_x, const uint8_t* d_pk_odd, const uint8_t* d_msgs, const uint8_t* d_sigs,
                        uint32_t n, int hash_kind, uint8_t* d_out);
 
+// batch of PrivateKey::to_pub + sign; status[i] in {1, 2 = "Invalid repr" in the reference}
+int32_t bjj_sign_dev(og_ctx* ctx, const uint8_t* d_sk, const uint8_t* d_rnd, const uint8_t* d_msgs, uint32_t n, int hash_kind,
+                     uint8_t* d_pk_x, uint8_t* d_pk_odd, uint8_t* d_sigs, uint8_t* d_status);
+
 }  // namespace og

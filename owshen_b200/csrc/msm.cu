@@ -120,7 +120,9 @@ struct DigitIter {
     }
 };
 
-// one thread per scalar, global atomics (one-shot MSMs: up to 2^15 buckets x 16 windows of keys)
+// one thread per scalar.  The scatter is pure memory latency (ncu, profiles/r2_ncu_digits.md: 93 % of the warp samples wait on
+// the atomic's round trip, issue slots 17 % busy), so the digits of EIGHT windows are cut first, their eight cursor atomics
+// issued back to back and only then the eight dependent 4-byte stores: eight round trips in flight per thread instead of one.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                                                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
@@ -129,15 +131,38 @@ __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restric
     if (i >= P.n) return;
     DigitIter it;
     if (!it.load(P, prob, i, flag)) return;
-    it.for_each(P, [&](uint32_t w, uint32_t b, uint32_t neg) {
-        uint32_t key = (prob * P.key_stride_problem + w * P.key_stride_window) * P.nb + b;
-        if (!SCATTER) {
-            atomicAdd(&counts[key], 1u);
-        } else {
-            uint32_t pos = atomicAdd(&cursor[key], 1u);          // cursor starts at the bucket's offset (k_scan_apply)
-            sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
+    const uint32_t c = P.c, half = 1u << (c - 1), mask = (1u << c) - 1;
+    const uint32_t key0 = prob * P.key_stride_problem;
+    uint32_t carry = 0;
+    for (uint32_t w0 = 0; w0 < P.n_windows; w0 += 8) {
+        uint32_t key[8], ent[8], pos[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t w = w0 + q;
+            key[q] = 0xffffffffu;
+            if (w < P.n_windows) {
+                uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
+                uint64_t two = ((uint64_t)it.s[word + 1] << 32) | it.s[word];
+                uint32_t v = ((uint32_t)(two >> sh) & mask) + carry;
+                uint32_t neg = v > half;
+                uint32_t mag = neg ? (1u << c) - v : v;
+                carry = neg;
+                if (mag) {
+                    key[q] = (key0 + w * P.key_stride_window) * P.nb + mag - 1;
+                    ent[q] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
+                }
+            }
         }
-    });
+        if (!SCATTER) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (key[q] != 0xffffffffu) atomicAdd(&counts[key[q]], 1u);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (key[q] != 0xffffffffu) pos[q] = atomicAdd(&cursor[key[q]], 1u);   // cursor starts at the bucket's offset (k_scan_apply)
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (key[q] != 0xffffffffu) sorted[pos[q]] = ent[q];
+        }
+    }
 }
 
 // Tiled histogram for the batched prover (one group per proof, nb <= 32768): a CTA owns a tile of one problem's
@@ -423,306 +448,91 @@ __global__ void __launch_bounds__(128, 6) k_bucket_acc_sm(const Affine<Fq2>* __r
 }
 #endif
 
+// Heavy buckets (lists above the cap: witness-like scalars put 30 % of all points into bucket "1" of window 0) are cut
+// into segments of `seg` entries; every segment gets a CTA, a second kernel adds the partial sums of each bucket.
+// Round 1 gave a whole list to ONE CTA: 3*10^5 entries on 256 threads were 5.5 of the 13.9 ms of a witness-like 2^20 MSM.
+// heavy[0] = number of heavy buckets, heavy[1 ..] = their keys, heavy[1 + n_keys ..] = first segment of each (+ total).
+template <class F>   // (template only so that each translation unit gets its own copy)
+__global__ void __launch_bounds__(256) k_heavy_plan(uint32_t* __restrict__ heavy, const uint32_t* __restrict__ counts, uint32_t n_keys, uint32_t seg) {
+    __shared__ uint32_t part[256];
+    __shared__ uint32_t carry;
+    const uint32_t n_heavy = heavy[0];
+    uint32_t* seg_base = heavy + 1 + n_keys;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_heavy; base += 256) {
+        uint32_t h = base + threadIdx.x;
+        uint32_t v = h < n_heavy ? (counts[heavy[1 + h]] + seg - 1) / seg : 0;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t d = 1; d < 256; d <<= 1) {
+            uint32_t t = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+            __syncthreads();
+            part[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (h < n_heavy) seg_base[h] = carry + part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry += part[255];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg_base[n_heavy] = carry;
+}
+
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_bucket_heavy(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
                                                           const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
-                                                          XYZZ<F>* __restrict__ buckets, const uint32_t* __restrict__ heavy) {
+                                                          uint32_t n_keys, uint32_t seg, XYZZ<F>* __restrict__ partials,
+                                                          const uint32_t* __restrict__ heavy) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     XYZZ<F>* sh = reinterpret_cast<XYZZ<F>*>(smem_raw);
-    uint32_t n_heavy = heavy[0];
-    for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
-        uint32_t key = heavy[1 + h];
-        uint32_t cnt = counts[key], off = offsets[key];
+    const uint32_t n_heavy = heavy[0];
+    const uint32_t* seg_base = heavy + 1 + n_keys;
+    const uint32_t n_seg = n_heavy ? seg_base[n_heavy] : 0;
+    for (uint32_t g = blockIdx.x; g < n_seg; g += gridDim.x) {
+        uint32_t lo = 0, hi = n_heavy;                          // largest h with seg_base[h] <= g
+        while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (seg_base[mid] <= g) lo = mid; else hi = mid; }
+        const uint32_t key = heavy[1 + lo];
+        const uint32_t cnt = counts[key], off = offsets[key];
+        const uint32_t k0 = (g - seg_base[lo]) * seg, k1 = k0 + seg < cnt ? k0 + seg : cnt;
         XYZZ<F> acc = XYZZ<F>::inf();
-        for (uint32_t k = threadIdx.x; k < cnt; k += THREADS) { Affine<F> q = fetch_point(table, sorted[off + k]); xyzz_madd_ni(&acc, &q); }
+        for (uint32_t k = k0 + threadIdx.x; k < k1; k += THREADS) { Affine<F> q = fetch_point(table, sorted[off + k]); xyzz_madd_ni(&acc, &q); }
         sh[threadIdx.x] = acc;
         __syncthreads();
         for (int s = THREADS / 2; s > 0; s >>= 1) {
             if ((int)threadIdx.x < s) xyzz_add_ni(&sh[threadIdx.x], &sh[threadIdx.x + s]);
             __syncthreads();
         }
-        if (threadIdx.x == 0) buckets[key] = sh[0];
+        if (threadIdx.x == 0) partials[g] = sh[0];
         __syncthreads();
     }
 }
 
-// ---- 4b: batched-affine bucket accumulation (the batched prover; profiles/r2_affine_ab.md) ------------------------
-// A mixed XYZZ addition costs 8M + 2S; an affine addition costs 1M + 1S + 1M once 1/(x2 - x1) is known, and Montgomery's
-// trick turns N inversions into one inversion and 3(N-1) products.  With 10^7 buckets per chunk there are 10^7 independent
-// additions available at every step of the bucket lists, so the accumulation runs in ROUNDS: round j adds entry j of every
-// bucket list to that bucket's affine accumulator (64 B in HBM).  One kernel per round, k_aff_round:
-//   * a thread owns AFF_KB neighbouring buckets of the load-ordered list, a CTA 128 threads;
-//   * prologue: the CTA rebuilds the product tree of its threads' denominator products in shared memory and walks it down
-//     from 1/(CTA product) -- supplied by the tiny batched inversion over CTA products that runs between rounds
-//     (two 32-fold tree levels + Fermat on <= ~1000 values) -- to every thread's own inverse u;
-//   * main loop: inv_d = u * pre[slot]; u *= d; lambda, x3, y3; then the denominator of the NEXT round from the fresh
-//     accumulator, its running product stored as pre[slot].  The loop direction alternates between rounds so that the
-//     exclusive products written by one round are exactly what the next one peels (no second pass, no recomputation);
-//   * epilogue: per-thread products -> CTA product.
-// Per addition 5M + 1S (+ ~0.3M of trees and inversion) against 8M + 2S; in exchange the accumulator (64 B read + 64 B
-// write) and pre (32 B + 32 B) travel through HBM every round -- multiplier time traded for bandwidth the XYZZ kernel
-// leaves idle.  Exceptional cases (P + P, P - P, infinity) keep the batch alive by contributing no denominator (or 2y
-// for a doubling) and are resolved per slot.  Infinity in the accumulator array is x.l[7] = 0xffffffff (no reduced field
-// element looks like that), so a slot is classified from x coordinates alone unless they collide.
-constexpr int AFF_KB = 8, AFF_THREADS = 128;
-constexpr uint32_t AFF_INF_MARK = 0xffffffffu;
-
-template <class F> struct AffMark;
-template <> struct AffMark<Fq> {
-    static __device__ __forceinline__ bool is_inf(const Fq& x) { return x.l[7] == AFF_INF_MARK; }
-    static __device__ __forceinline__ void set_inf(Fq& x) { x.l[7] = AFF_INF_MARK; }
-};
-template <> struct AffMark<Fq2> {
-    static __device__ __forceinline__ bool is_inf(const Fq2& x) { return x.c0.l[7] == AFF_INF_MARK; }
-    static __device__ __forceinline__ void set_inf(Fq2& x) { x.c0.l[7] = AFF_INF_MARK; }
-};
-
-enum : int { AFF_SKIP = 0, AFF_SET = 1, AFF_ADD = 2, AFF_DBL = 3, AFF_ZERO = 4 };
-
-// what adding table point `e` does to an accumulator with x = ax, and the denominator d it needs (ADD / DBL only)
+// buckets[key] = sum of the bucket's segment sums (one warp per heavy bucket)
 template <class F>
-__device__ __forceinline__ int aff_classify(const Affine<F>* __restrict__ table, uint32_t e, const F& ax, const Affine<F>* acc_slot, F& px, F& d) {
-    const Affine<F>* tp = table + (e >> 1);
-    px = tp->x;
-    if (px.is_zero() && tp->y.is_zero()) return AFF_SKIP;           // table point at infinity
-    if (AffMark<F>::is_inf(ax)) return AFF_SET;
-    d = px - ax;
-    if (!d.is_zero()) return AFF_ADD;
-    F py = tp->y;
-    if (e & 1) py = py.neg();
-    F ay = acc_slot->y;
-    if (py == ay) { d = ay.dbl(); return AFF_DBL; }                   // y != 0 on these curves (odd group order)
-    return AFF_ZERO;
-}
-
-// slot-ordered (= load-ordered) copies of the list offsets / lengths; buckets above the cap go to k_bucket_heavy
-template <class F>
-__global__ void __launch_bounds__(128) k_aff_slots(const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts, uint32_t n_keys,
-                                                   uint32_t cap, const uint32_t* __restrict__ perm, uint32_t* __restrict__ slot_off,
-                                                   uint32_t* __restrict__ slot_cnt, uint32_t* __restrict__ heavy, F* __restrict__ cta_tot, uint32_t n_cta) {
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot < n_cta) cta_tot[slot] = F::one();
-    if (slot >= n_keys) return;
-    uint32_t key = perm[slot];
-    uint32_t cnt = counts[key];
-    if (cnt > cap) {
-        uint32_t h = atomicAdd(heavy, 1u);
-        heavy[1 + h] = key;
-        cnt = 0;
-    }
-    slot_off[slot] = offsets[key];
-    slot_cnt[slot] = cnt;
-}
-
-// shared-memory product tree over the CTA's 128 per-thread values (heap order: node i has children 2i and 2i + 1,
-// leaves at 128 .. 255); returns the root in node[1]
-template <class F>
-__device__ __forceinline__ void aff_tree_up(F* node, const F& leaf) {
-    node[AFF_THREADS + threadIdx.x] = leaf;
-    for (uint32_t w = AFF_THREADS / 2; w >= 1; w >>= 1) {
-        __syncthreads();
-        if (threadIdx.x < w) { uint32_t i = w + threadIdx.x; node[i] = node[2 * i] * node[2 * i + 1]; }
-    }
-    __syncthreads();
-}
-
-// round j (FIRST: j = 0 loads entry 0 into the accumulators).  leaves[t]: product of thread t's denominators for THIS
-// round on entry, for the next round on exit; cta_inv[c] = 1 / (product over CTA c) for this round; cta_tot[c] receives
-// the CTA product for the next round.
-template <class F, bool FIRST, int MINB>
-__global__ void __launch_bounds__(AFF_THREADS, MINB) k_aff_round(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
-                                                           const uint32_t* __restrict__ slot_off, const uint32_t* __restrict__ slot_cnt,
-                                                           uint32_t n_keys, uint32_t j, Affine<F>* __restrict__ acc, F* __restrict__ pre,
-                                                           F* __restrict__ leaves, const F* __restrict__ cta_inv, F* __restrict__ cta_tot) {
-    __shared__ F node[2 * AFF_THREADS];
-    __shared__ F ninv[2 * AFF_THREADS];
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t s0 = t * AFF_KB;
-    uint32_t mx = 0;
-#pragma unroll
-    for (int k = 0; k < AFF_KB; k++) {
-        uint32_t c = s0 + k < n_keys ? slot_cnt[s0 + k] : 0;
-        mx = c > mx ? c : mx;
-    }
-    const bool mine = mx > j;
-    if (!__syncthreads_or(mine)) return;           // nothing in this CTA this round, hence nothing later: its product stays 1
-    F u = F::one();
-    if (!FIRST) {
-        aff_tree_up(node, mine ? leaves[t] : F::one());
-        if (threadIdx.x == 0) ninv[1] = cta_inv[blockIdx.x];
-        for (uint32_t w = 2; w <= AFF_THREADS; w <<= 1) {
-            __syncthreads();
-            if (threadIdx.x < w) { uint32_t i = w + threadIdx.x; ninv[i] = ninv[i >> 1] * node[i ^ 1]; }
+__global__ void __launch_bounds__(32) k_heavy_combine(const XYZZ<F>* __restrict__ partials, uint32_t n_keys, XYZZ<F>* __restrict__ buckets,
+                                                      const uint32_t* __restrict__ heavy) {
+    __shared__ XYZZ<F> sh[32];
+    const uint32_t n_heavy = heavy[0];
+    const uint32_t* seg_base = heavy + 1 + n_keys;
+    for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        const uint32_t s0 = seg_base[h], s1 = seg_base[h + 1];
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t s = s0 + threadIdx.x; s < s1; s += 32) xyzz_add_ni(&acc, &partials[s]);
+        sh[threadIdx.x] = acc;
+        __syncwarp();
+        for (int w = 16; w > 0; w >>= 1) {
+            if ((int)threadIdx.x < w) xyzz_add_ni(&sh[threadIdx.x], &sh[threadIdx.x + w]);
+            __syncwarp();
         }
-        __syncthreads();
-        u = ninv[AFF_THREADS + threadIdx.x];
+        if (threadIdx.x == 0) buckets[heavy[1 + h]] = sh[0];
+        __syncwarp();
     }
-    F run = F::one();
-    if (mine) {
-#pragma unroll 1
-        for (int kk = 0; kk < AFF_KB; kk++) {
-            const int k = (j & 1) ? AFF_KB - 1 - kk : kk;
-            const uint32_t slot = s0 + k;
-            if (slot >= n_keys) continue;
-            const uint32_t cnt = slot_cnt[slot];
-            if (cnt <= j) continue;
-            const uint32_t off = slot_off[slot];
-            const uint32_t e = sorted[off + j];
-            Affine<F> r;
-            bool r_has_y = true;
-            if (FIRST) {
-                r = fetch_point(table, e);
-                if (r.is_inf()) AffMark<F>::set_inf(r.x);
-                acc[slot] = r;
-            } else {
-                F ax = acc[slot].x, px, d;
-                int kind = aff_classify(table, e, ax, acc + slot, px, d);
-                if (kind == AFF_SKIP) {
-                    r.x = ax; r_has_y = false;
-                } else if (kind == AFF_SET) {
-                    r = fetch_point(table, e);
-                    acc[slot] = r;
-                } else if (kind == AFF_ZERO) {
-                    r = Affine<F>::inf(); AffMark<F>::set_inf(r.x);
-                    acc[slot] = r;
-                } else {
-                    F inv_d = u * pre[slot];
-                    u = u * d;
-                    F py = table[e >> 1].y;
-                    if (e & 1) py = py.neg();
-                    F ay = acc[slot].y;
-                    F num;
-                    if (kind == AFF_ADD) num = py - ay;
-                    else { F xx = ax.sqr(); num = xx.dbl() + xx; }
-                    F lam = num * inv_d;
-                    r.x = lam.sqr() - ax - px;
-                    r.y = lam * (ax - r.x) - ay;
-                    acc[slot] = r;
-                }
-            }
-            if (cnt > j + 1) {                      // denominator of the next round from the fresh accumulator
-                const uint32_t e2 = sorted[off + j + 1];
-                F px2, d2;
-                Affine<F> rr;
-                if (!r_has_y) rr.y = acc[slot].y;
-                else rr.y = r.y;
-                int k2 = aff_classify(table, e2, r.x, &rr, px2, d2);
-                if (k2 == AFF_ADD || k2 == AFF_DBL) { pre[slot] = run; run = run * d2; }
-            }
-        }
-    }
-    if (mine) leaves[t] = run;
-    aff_tree_up(node, run);
-    if (threadIdx.x == 0) cta_tot[blockIdx.x] = node[1];
 }
 
-// after the last round: remaining entries (lists longer than the round count) serially in XYZZ, result to key order
-template <class F>
-__global__ void __launch_bounds__(128) k_aff_finish(const Affine<F>* __restrict__ table, const uint32_t* __restrict__ sorted,
-                                                    const uint32_t* __restrict__ slot_off, const uint32_t* __restrict__ slot_cnt,
-                                                    const uint32_t* __restrict__ counts, uint32_t n_keys, uint32_t cap, uint32_t rounds,
-                                                    const uint32_t* __restrict__ perm, const Affine<F>* __restrict__ acc,
-                                                    XYZZ<F>* __restrict__ buckets) {
-    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= n_keys) return;
-    uint32_t key = perm[slot];
-    if (counts[key] > cap) return;                  // heavy: k_bucket_heavy owns buckets[key]
-    uint32_t cnt = slot_cnt[slot], off = slot_off[slot];
-    XYZZ<F> r = XYZZ<F>::inf();
-    if (cnt) {
-        Affine<F> a = acc[slot];
-        if (!AffMark<F>::is_inf(a.x)) r = XYZZ<F>{a.x, a.y, F::one(), F::one()};
-    }
-    for (uint32_t k = rounds; k < cnt; k++) { Affine<F> q = fetch_point(table, sorted[off + k]); xyzz_madd_ni(&r, &q); }
-    buckets[key] = r;
-}
-
-// ---- batched inversion of n field elements in place: two tree levels of INV_E-fold products, Fermat at the top -------
-constexpr uint32_t INV_E = 32;
-template <class F>
-__global__ void __launch_bounds__(64) k_inv_up(const F* __restrict__ v, uint64_t n, F* __restrict__ prefix, F* __restrict__ group) {
-    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t lo = g * INV_E, hi = lo + INV_E < n ? lo + INV_E : n;
-    if (lo >= n) return;
-    F p = F::one();
-    for (uint64_t i = lo; i < hi; i++) { prefix[i] = p; p = p * v[i]; }
-    group[g] = p;
-}
-template <class F>
-__global__ void __launch_bounds__(64) k_inv_down(F* __restrict__ v, uint64_t n, const F* __restrict__ prefix, const F* __restrict__ group_inv) {
-    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t lo = g * INV_E, hi = lo + INV_E < n ? lo + INV_E : n;
-    if (lo >= n) return;
-    F u = group_inv[g];
-    for (uint64_t i = hi; i-- > lo;) { F e = v[i]; v[i] = u * prefix[i]; u = u * e; }
-}
-template <class F>
-__global__ void __launch_bounds__(32) k_inv_fermat(F* __restrict__ v, uint64_t n) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = v[i].inv();
-}
-
-// scratch (F elements): n prefix + n/E groups + n/E prefix + n/E^2 groups
-static inline size_t inv_scratch_elems(uint64_t n) { uint64_t n1 = (n + INV_E - 1) / INV_E, n2 = (n1 + INV_E - 1) / INV_E; return n + 2 * n1 + n2 + 8; }
-
-// out[i] = 1 / v[i]  (v is left untouched only when out != v)
-template <class F>
-static int32_t batch_invert(og_ctx* ctx, const F* v, F* out, uint64_t n, F* scratch) {
-    if (n == 0) return OG_OK;
-    uint64_t n1 = (n + INV_E - 1) / INV_E, n2 = (n1 + INV_E - 1) / INV_E;
-    F *pre0 = scratch, *g1 = pre0 + n, *pre1 = g1 + n1, *g2 = pre1 + n1;
-    if (out != v) OG_CUDA(ctx, cudaMemcpyAsync(out, v, sizeof(F) * n, cudaMemcpyDeviceToDevice, ctx->stream));
-    OG_LAUNCHN(ctx, "k_inv_up", k_inv_up<F>, (unsigned)((n1 + 63) / 64), 64, 0, out, n, pre0, g1);
-    OG_LAUNCHN(ctx, "k_inv_up", k_inv_up<F>, (unsigned)((n2 + 63) / 64), 64, 0, g1, n1, pre1, g2);
-    OG_LAUNCHN(ctx, "k_inv_fermat", k_inv_fermat<F>, (unsigned)((n2 + 31) / 32), 32, 0, g2, n2);
-    OG_LAUNCHN(ctx, "k_inv_down", k_inv_down<F>, (unsigned)((n2 + 63) / 64), 64, 0, g1, n1, pre1, g2);
-    OG_LAUNCHN(ctx, "k_inv_down", k_inv_down<F>, (unsigned)((n1 + 63) / 64), 64, 0, out, n, pre0, g1);
-    return OG_OK;
-}
-
-// bytes of scratch msm_buckets needs for the batched-affine accumulation of n_keys buckets
-template <class F>
-static size_t aff_scratch_bytes_t(uint64_t n_keys) {
-    uint64_t n_thr = (n_keys + AFF_KB - 1) / AFF_KB, n_cta = (n_thr + AFF_THREADS - 1) / AFF_THREADS;
-    return (sizeof(Affine<F>) + sizeof(F) + 8) * n_keys + sizeof(F) * (n_thr + 2 * n_cta + inv_scratch_elems(n_cta)) + 4096;
-}
-
-template <class F>
-static int32_t bucket_acc_affine(og_ctx* ctx, const Affine<F>* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
-                                 const uint32_t* d_counts, uint32_t n_keys, uint32_t cap, uint64_t avg, XYZZ<F>* d_buckets,
-                                 uint32_t* d_heavy, const uint32_t* d_perm, void* scratch) {
-    const uint32_t n_thr = (n_keys + AFF_KB - 1) / AFF_KB, n_cta = (n_thr + AFF_THREADS - 1) / AFF_THREADS;
-    unsigned char* p = static_cast<unsigned char*>(scratch);
-    Affine<F>* acc = reinterpret_cast<Affine<F>*>(p); p += sizeof(Affine<F>) * (size_t)n_keys;
-    F* pre = reinterpret_cast<F*>(p); p += sizeof(F) * (size_t)n_keys;
-    F* leaves = reinterpret_cast<F*>(p); p += sizeof(F) * (size_t)n_thr;
-    F* cta_tot = reinterpret_cast<F*>(p); p += sizeof(F) * (size_t)n_cta;
-    F* cta_inv = reinterpret_cast<F*>(p); p += sizeof(F) * (size_t)n_cta;
-    F* inv_scr = reinterpret_cast<F*>(p); p += sizeof(F) * inv_scratch_elems(n_cta);
-    uint32_t* slot_off = reinterpret_cast<uint32_t*>(p); p += 4 * (size_t)n_keys;
-    uint32_t* slot_cnt = reinterpret_cast<uint32_t*>(p);
-    // rounds: the lists are ~Poisson(avg); beyond avg + 4 sigma + 2 the few remaining entries are cheaper in k_aff_finish
-    uint32_t rounds = 0;
-    { const char* v = getenv("OG_AFF_ROUNDS"); if (v) rounds = (uint32_t)atoi(v); }
-    if (!rounds) { uint32_t sig = 1; while ((uint64_t)sig * sig < avg) sig++; rounds = (uint32_t)avg + 4 * sig + 2; }
-    if (rounds > cap) rounds = cap;                 // entries 0 .. rounds-1 of every list are consumed by rounds 0 .. rounds-1
-    const bool g1 = sizeof(F) == 32;
-    OG_LAUNCHN(ctx, g1 ? "k_aff_slots_g1" : "k_aff_slots_g2", k_aff_slots<F>, (n_keys + 127) / 128, 128, 0, d_offsets, d_counts, n_keys, cap, d_perm,
-               slot_off, slot_cnt, d_heavy, cta_tot, n_cta);
-    const char* kn = g1 ? "k_bucket_acc_g1" : "k_bucket_acc_g2";
-    { auto k0 = k_aff_round<F, true, 1>; OG_LAUNCHN(ctx, kn, k0, n_cta, AFF_THREADS, 0, d_table, d_sorted, slot_off, slot_cnt, n_keys, 0u, acc, pre, leaves, cta_inv, cta_tot); }
-    for (uint32_t j = 1; j < rounds; j++) {
-        OG_TRY(batch_invert<F>(ctx, cta_tot, cta_inv, n_cta, inv_scr));
-        // resident CTAs per SM requested from ptxas (registers <-> warps in flight): measured, OG_AFF_OCC = 5 | 6 | 8
-        static const int occ = [] { const char* v = getenv("OG_AFF_OCC"); return v ? atoi(v) : 0; }();
-        if (g1 && occ == 6) { auto k1 = k_aff_round<F, false, (sizeof(F) == 32 ? 6 : 2)>; OG_LAUNCHN(ctx, kn, k1, n_cta, AFF_THREADS, 0, d_table, d_sorted, slot_off, slot_cnt, n_keys, j, acc, pre, leaves, cta_inv, cta_tot); }
-        else if (g1 && occ == 8) { auto k1 = k_aff_round<F, false, (sizeof(F) == 32 ? 8 : 2)>; OG_LAUNCHN(ctx, kn, k1, n_cta, AFF_THREADS, 0, d_table, d_sorted, slot_off, slot_cnt, n_keys, j, acc, pre, leaves, cta_inv, cta_tot); }
-        else { auto k1 = k_aff_round<F, false, (sizeof(F) == 32 ? 5 : 2)>; OG_LAUNCHN(ctx, kn, k1, n_cta, AFF_THREADS, 0, d_table, d_sorted, slot_off, slot_cnt, n_keys, j, acc, pre, leaves, cta_inv, cta_tot); }
-    }
-    OG_LAUNCHN(ctx, g1 ? "k_aff_finish_g1" : "k_aff_finish_g2", k_aff_finish<F>, (n_keys + 127) / 128, 128, 0, d_table, d_sorted, slot_off, slot_cnt, d_counts,
-               n_keys, cap, rounds, d_perm, acc, d_buckets);
-    return OG_OK;
-}
+#ifdef OG_EXPERIMENT_AFFINE
+#include "experiments/bucket_affine.cuh"      // rejected in round 2 (profiles/r2_affine_ab.md); not in the shipped library
+#endif
 
 constexpr uint32_t RED_FAN_LOG2 = 3, RED_FAN = 1u << RED_FAN_LOG2;   // 8 children per parent: more threads, shorter chains
 // ---- 5: weighted reduction, RED_FAN children per parent -------------------------------------------------------
@@ -733,8 +543,25 @@ constexpr uint32_t RED_FAN_LOG2 = 3, RED_FAN = 1u << RED_FAN_LOG2;   // 8 childr
 // accumulator fewer to keep in registers.  (A variant with R and T in shared memory -- 128 instead of 226 registers,
 // twice the resident warps -- was measured slower, 32.7 vs 30.7 ms per step for G1: the R -> T chain, not occupancy,
 // is what this kernel waits on.)
-template <class F, bool HAS_U>
-__global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
+// Group operations of the reduction.  G1: ONE out-of-line copy of add and dbl with operands and result in registers (by
+// value): the fully inlined kernel (three adds and a doubling, ~13k instructions) spent 15 % of its warp samples waiting for
+// instructions (ncu, profiles/r2_ncu_reduce.md) at 8 resident warps per SM.  G2 keeps the inlined group law over the
+// out-of-line Fq2 multiplier (128 registers of arguments would not travel in registers).
+template <class F> struct RedOps {
+    static __device__ __forceinline__ void add(XYZZ<F>& a, const XYZZ<F>& b) { a.add(b); }
+    static __device__ __forceinline__ void dbl(XYZZ<F>& a) { a = a.dbl(); }
+};
+#ifdef OG_MSM_G1
+static __device__ __noinline__ XYZZ<Fq> g1_add_rv(XYZZ<Fq> a, XYZZ<Fq> b) { a.add(b); return a; }
+static __device__ __noinline__ XYZZ<Fq> g1_dbl_rv(XYZZ<Fq> a) { return a.dbl(); }
+template <> struct RedOps<Fq> {
+    static __device__ __forceinline__ void add(XYZZ<Fq>& a, const XYZZ<Fq>& b) { a = g1_add_rv(a, b); }
+    static __device__ __forceinline__ void dbl(XYZZ<Fq>& a) { a = g1_dbl_rv(a); }
+};
+#endif
+
+template <class F, bool HAS_U, int MINB>
+__global__ void __launch_bounds__(64, MINB) k_reduce_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
                                                      uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
                                                      uint32_t fan_log2, XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ U_out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -742,18 +569,16 @@ __global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__
     uint32_t g = t / n_out, p = t % n_out;
     const XYZZ<F>* S = S_in + (size_t)g * n_in;
     uint32_t lo = p << fan_log2, hi = min(n_in, lo + (1u << fan_log2));
-    // group operations inlined here: with 2^15 buckets per proof this kernel is 10 % of a proving step, and the
-    // out-of-line versions move every operand through local memory
     XYZZ<F> R = XYZZ<F>::inf(), T = XYZZ<F>::inf();
     for (uint32_t i = hi - 1; i > lo; i--) {
-        R.add(S[i]);
-        T.add(R);
+        RedOps<F>::add(R, S[i]);
+        RedOps<F>::add(T, R);
     }
-    R.add(S[lo]);
-    for (uint32_t k = 0; k < w_log2; k++) T = T.dbl();
+    RedOps<F>::add(R, S[lo]);
+    for (uint32_t k = 0; k < w_log2; k++) RedOps<F>::dbl(T);
     if (HAS_U) {
         const XYZZ<F>* U = U_in + (size_t)g * n_in;
-        for (uint32_t i = lo; i < hi; i++) T.add(U[i]);
+        for (uint32_t i = lo; i < hi; i++) RedOps<F>::add(T, U[i]);
     }
     S_out[(size_t)g * n_out + p] = R;
     U_out[(size_t)g * n_out + p] = T;
@@ -782,9 +607,12 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
     // (skewed scalars: witness 0/1 values, short scalars whose top window has few distinct digits)
     uint64_t avg = n_entries_max / (n_keys ? n_keys : 1);
     uint32_t cap = (uint32_t)(4 * avg < 128 ? 128 : 4 * avg);
+#ifdef OG_EXPERIMENT_AFFINE
     if (aff_scratch) {
         OG_TRY((bucket_acc_affine<F>(ctx, d_table, d_sorted, d_offsets, d_counts, n_keys, cap, avg, d_buckets, d_heavy, d_perm, aff_scratch)));
-    } else {
+    } else
+#endif
+    {
         // the long issue-bound kernel of the MSM: on the lane's low-priority stream when the prover runs chunks in flight
         const char* kn = sizeof(F) == 32 ? "k_bucket_acc_g1" : "k_bucket_acc_g2";
         unsigned grid = (n_keys + 127) / 128;
@@ -802,8 +630,16 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
         OG_TRY(rc);
         if (ctx->acc_stream) OG_CUDA(ctx, stream_handoff(ctx->acc_ev, ctx->acc_stream, hi));
     }
-    auto k_heavy = k_bucket_heavy<F, HT>;
-    OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_bucket_heavy_g1" : "k_bucket_heavy_g2", k_heavy, ctx->sm_count, HT, HT * sizeof(XYZZ<F>), d_table, d_sorted, d_offsets, d_counts, d_buckets, d_heavy);
+    {
+        // segment length: long enough that the segment sums of ALL heavy buckets fit in the (still unused) reduction scratch
+        // (at most n_keys / 4 heavy buckets, since each holds more than 4 x the average load)
+        uint32_t seg = (uint32_t)(4 * avg < 2048 ? 2048 : 4 * avg);
+        auto k_heavy = k_bucket_heavy<F, HT>;
+        OG_LAUNCHN(ctx, "k_heavy_plan", k_heavy_plan<F>, 1, 256, 0, d_heavy, d_counts, n_keys, seg);
+        OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_bucket_heavy_g1" : "k_bucket_heavy_g2", k_heavy, 4 * ctx->sm_count, HT, HT * sizeof(XYZZ<F>), d_table, d_sorted,
+                   d_offsets, d_counts, n_keys, seg, d_lvl, d_heavy);
+        OG_LAUNCH(ctx, k_heavy_combine<F>, ctx->sm_count, 32, 0, d_lvl, n_keys, d_buckets, d_heavy);
+    }
     // reduction levels
     size_t lvl_stride = (size_t)n_groups * ((nb + RED_FAN - 1) / RED_FAN) + 16;
     XYZZ<F>* bufS[2] = {d_lvl, d_lvl + lvl_stride};
@@ -820,8 +656,13 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
         uint32_t n_out = (n_in + (1u << fan_log2) - 1) >> fan_log2;
         uint32_t threads = n_groups * n_out;
         const char* rn = sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2";
-        if (U_in) { auto k = k_reduce_level<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
-        else { auto k = k_reduce_level<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+        // resident 64-thread CTAs per SM asked of ptxas (G1: 4 = 206 registers, 6 = 168, 8 = 128 with spills): OG_RED_OCC
+        static const int rocc = [] { const char* v = getenv("OG_RED_OCC"); return v ? atoi(v) : 0; }();
+#define OG_RED_LAUNCH(HASU, MB) { auto k = k_reduce_level<F, HASU, MB>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+        if (sizeof(F) == 32 && rocc == 6) { if (U_in) OG_RED_LAUNCH(true, 6) else OG_RED_LAUNCH(false, 6) }
+        else if (sizeof(F) == 32 && rocc == 8) { if (U_in) OG_RED_LAUNCH(true, 8) else OG_RED_LAUNCH(false, 8) }
+        else { if (U_in) OG_RED_LAUNCH(true, 1) else OG_RED_LAUNCH(false, 1) }
+#undef OG_RED_LAUNCH
         S_in = bufS[pp]; U_in = bufU[pp];
         pp ^= 1;
         n_in = n_out;
@@ -837,7 +678,11 @@ int32_t msm_buckets_g1(og_ctx* ctx, const G1Affine* d_table, const uint32_t* d_s
                        G1XYZZ* d_lvl, uint32_t* d_heavy, uint32_t* d_perm, G1XYZZ* d_totals, void* aff_scratch) {
     return msm_buckets<Fq>(ctx, d_table, d_sorted, d_offsets, d_counts, n_groups, nb, n_entries_max, d_buckets, d_lvl, d_heavy, d_perm, d_totals, aff_scratch);
 }
+#ifdef OG_EXPERIMENT_AFFINE
 size_t msm_aff_scratch_bytes_g1(uint64_t n_keys) { return aff_scratch_bytes_t<Fq>(n_keys); }
+#else
+size_t msm_aff_scratch_bytes_g1(uint64_t) { return 0; }
+#endif
 #endif  // OG_MSM_G1
 
 #ifdef OG_MSM_G2
@@ -846,7 +691,11 @@ int32_t msm_buckets_g2(og_ctx* ctx, const G2Affine* d_table, const uint32_t* d_s
                        G2XYZZ* d_lvl, uint32_t* d_heavy, uint32_t* d_perm, G2XYZZ* d_totals, void* aff_scratch) {
     return msm_buckets<Fq2>(ctx, d_table, d_sorted, d_offsets, d_counts, n_groups, nb, n_entries_max, d_buckets, d_lvl, d_heavy, d_perm, d_totals, aff_scratch);
 }
+#ifdef OG_EXPERIMENT_AFFINE
 size_t msm_aff_scratch_bytes_g2(uint64_t n_keys) { return aff_scratch_bytes_t<Fq2>(n_keys); }
+#else
+size_t msm_aff_scratch_bytes_g2(uint64_t) { return 0; }
+#endif
 #endif  // OG_MSM_G2
 
 
@@ -890,7 +739,7 @@ static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sc
     OG_SLOT(ctx, sorted, uint32_t, S_MSM_SORTED, 4 * (size_t)n * W);
     OG_SLOT(ctx, buckets, XYZZ<F>, S_MSM_BUCKETS, sizeof(XYZZ<F>) * (size_t)n_keys);
     OG_SLOT(ctx, lvl, XYZZ<F>, S_MSM_SEG, sizeof(XYZZ<F>) * msm_lvl_elems(W, nb));
-    OG_SLOT(ctx, heavy, uint32_t, S_MSM_HEAVY, 4 * ((size_t)n_keys + 1));
+    OG_SLOT(ctx, heavy, uint32_t, S_MSM_HEAVY, 4 * (2 * (size_t)n_keys + 4));
     OG_SLOT(ctx, totals, XYZZ<F>, S_MSM_OUT, sizeof(XYZZ<F>) * W);
     OG_LAUNCH(ctx, k_points_to_mont<F>, (unsigned)((n + 127) / 128), 128, 0, d_points, n, pts, ctx->d_flag);
     DigitPlan plan;
@@ -900,13 +749,13 @@ static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sc
     plan.key_stride_problem = 0; plan.key_stride_window = 1; plan.tidx_window_stride = 0;
     plan.montgomery = 0;
     OG_TRY(msm_sort_digits(ctx, plan, n_keys, counts, offsets, cursor, sorted));
-    // one-shot MSMs keep the XYZZ accumulation (too few buckets to amortise ~60 rounds of launches); OG_AFFINE_ONESHOT=1
-    // routes them through the batched-affine kernels so that the edge-case tests exercise those too
     void* aff = nullptr;
-    {
+#ifdef OG_EXPERIMENT_AFFINE
+    {   // OG_AFFINE_ONESHOT=1 routes one-shot MSMs through the experiment so that the edge-case tests exercise it
         const char* v = getenv("OG_AFFINE_ONESHOT");
         if (v && atoi(v) > 0) { aff = ctx->slot(S_MSM_AFF, aff_scratch_bytes_t<F>(n_keys)); if (!aff) return OG_E_NOMEM; }
     }
+#endif
     OG_TRY((msm_buckets<F>(ctx, pts, sorted, offsets, counts, W, nb, n * W, buckets, lvl, heavy, cursor, totals, aff)));
     OG_LAUNCH(ctx, k_horner<F>, 1, 32, 0, totals, W, c, d_out);
     return OG_OK;

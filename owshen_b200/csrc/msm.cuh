@@ -31,7 +31,7 @@ int32_t msm_sort_digits(og_ctx* ctx, const DigitPlan& plan, uint32_t n_keys, uin
 
 // Accumulate every bucket and reduce each group to sum_b (b+1) * bucket_b.
 // d_buckets: n_groups * nb XYZZ scratch; d_lvl: msm_lvl_elems(n_groups, nb) XYZZ scratch;
-// d_heavy: n_keys + 1 u32 scratch; n_entries_max: upper bound on the sorted entries (sets the heavy-bucket cap);
+// d_heavy: 2 * n_keys + 4 u32 scratch; n_entries_max: upper bound on the sorted entries (sets the heavy-bucket cap);
 // d_perm: n_keys u32 scratch (the sort's cursor array may be reused); result: d_totals[n_groups].
 int32_t msm_buckets_g1(og_ctx* ctx, const G1Affine* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
                        const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, uint64_t n_entries_max, G1XYZZ* d_buckets,
@@ -39,8 +39,8 @@ int32_t msm_buckets_g1(og_ctx* ctx, const G1Affine* d_table, const uint32_t* d_s
 int32_t msm_buckets_g2(og_ctx* ctx, const G2Affine* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
                        const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, uint64_t n_entries_max, G2XYZZ* d_buckets,
                        G2XYZZ* d_lvl, uint32_t* d_heavy, uint32_t* d_perm, G2XYZZ* d_totals, void* aff_scratch = nullptr);
-// aff_scratch != nullptr selects the batched-affine accumulation (rounds over affine accumulators in HBM, one batched
-// inversion per round) instead of the one-thread-per-bucket XYZZ kernel; it must hold msm_aff_scratch_bytes_*(n_keys) bytes
+// aff_scratch: experiment builds only (-DOG_EXPERIMENT_AFFINE): non-null selects the rejected batched-affine accumulation
+// (csrc/experiments/bucket_affine.cuh, profiles/r2_affine_ab.md); the shipped library ignores it and the sizes are 0
 size_t msm_aff_scratch_bytes_g1(uint64_t n_keys);
 size_t msm_aff_scratch_bytes_g2(uint64_t n_keys);
 static inline size_t msm_lvl_elems(uint32_t n_groups, uint32_t nb) { return 4 * ((size_t)n_groups * ((nb + 7) / 8) + 16); }   // RED_FAN = 8

@@ -66,6 +66,29 @@ extern "C" void ht_bjj_verify(const uint8_t* pk_x, const uint8_t* pk_odd, const 
     }
 }
 
+// PrivateKey::to_pub + sign (bjj_core.cuh: bjj_sign_one) on the host, placeholder-product hash; and its integer step alone
+extern "C" void ht_bjj_sign(const uint8_t* sks, const uint8_t* rnds, const uint8_t* msgs, uint32_t n, const uint8_t* base_xy,
+                            uint8_t* pk_x, uint8_t* pk_odd, uint8_t* sigs, uint8_t* status) {
+    Fr bx = load<Fr>(base_xy), by = load<Fr>(base_xy + 32);
+    for (uint32_t i = 0; i < n; i++) {
+        Fr px, rx, ry, s;
+        bool odd;
+        status[i] = bjj_sign_one(load<Fr>(sks + 32 * i), load<Fr>(rnds + 32 * i), load<Fr>(msgs + 32 * i), bx, by,
+                                 [](const Fr* in) { return in[0] * in[1]; },
+                                 [](const Fr* in) { return in[0] * in[1] * in[2] * in[3] * in[4]; }, &px, &odd, &rx, &ry, &s);
+        store(pk_x + 32 * i, px); pk_odd[i] = odd ? 1 : 0;
+        store(sigs + 96 * i, rx); store(sigs + 96 * i + 32, ry); store(sigs + 96 * i + 64, s);
+    }
+}
+extern "C" void ht_bjj_s_mod_order(const uint8_t* r, const uint8_t* h, const uint8_t* a, uint8_t* out, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t rc[8], hc[8], ac[8], sc[8];
+        memcpy(rc, r + 32 * i, 32); memcpy(hc, h + 32 * i, 32); memcpy(ac, a + 32 * i, 32);
+        bjj_s_mod_order(sc, rc, hc, ac);
+        memcpy(out + 32 * i, sc, 32);
+    }
+}
+
 // ---- wide products / separate reduction (fp.cuh: mul_wide, sqr_wide, mont_reduce_wide) ----------------------
 extern "C" void ht_wide(const uint8_t* a, const uint8_t* b, uint8_t* mul32, uint8_t* sqr32, uint64_t n) {
     for (uint64_t i = 0; i < n; i++) {

@@ -92,3 +92,26 @@ def test_gpu_batch_verify_matches_oracle(ctx, hash_kind):
     assert list(ctx.bjj_verify_batch(*_pack([pk, pk], [123456, 123457], [sig, sig]))) == [1, 0]
     # undecompressible public key -> status 2 (the reference returns Err)
     assert list(ctx.bjj_verify_batch(*_pack([(3, 0)], [1], [sig]))) == [2]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hash_kind", [0, 1])
+def test_gpu_batch_sign_matches_oracle(ctx, hash_kind):
+    """og_bjj_sign_batch = PrivateKey::to_pub + PrivateKey::sign (mod.rs:206-237) for a batch of keys: public keys and
+    signatures equal the oracle's restatement bit for bit, verify on the GPU, and the reference's own test vector
+    (tests.rs:39-51: sk 12345, randomness 2345, message 123456) comes out the same."""
+    rng = random.Random(990 + hash_kind)
+    n = 40
+    sks = [rng.randrange(R) for _ in range(n - 3)] + [12345, 0, 1]
+    rnds = [rng.randrange(R) for _ in range(n - 3)] + [2345, 7, 0]
+    msgs = [rng.randrange(R) for _ in range(n - 3)] + [123456, 9, 11]
+    fb = bn.fr_to_bytes
+    pkx, odd, sigs, st = ctx.bjj_sign_batch(b"".join(map(fb, sks)), b"".join(map(fb, rnds)), b"".join(map(fb, msgs)), hash_kind)
+    assert list(st) == [1] * n
+    exp_pk = [bjj.to_pub(k) for k in sks]
+    exp_sig = [bjj.sign(k, r_, m, hash_kind) for k, r_, m in zip(sks, rnds, msgs)]
+    epx, eodd, em, es = _pack(exp_pk, msgs, exp_sig)
+    assert pkx == epx and odd == eodd and sigs == es
+    assert list(ctx.bjj_verify_batch(pkx, odd, em, sigs, hash_kind=hash_kind)) == [1] * n
+    with pytest.raises(ValueError):
+        ctx.bjj_sign_batch(bytes(32), bytes(31), bytes(32))

@@ -376,26 +376,12 @@ def test_merkle_append_and_rollback(ctx):
         ctx.merkle_append(2, 3, bytes(64), bytes(64), bytes(64))      # 2 leaves at index 3 of a 4-leaf tree
 
 
-def test_batched_affine_accumulation_matches_xyzz(ctx, keys32, monkeypatch):
-    """The batched-affine bucket accumulation (rounds of affine additions sharing one inversion) against the XYZZ kernel
-    and the oracle: the prover's three MSMs on a batch spanning two chunks, and -- through OG_AFFINE_ONESHOT -- the
-    one-shot MSM edge cases (infinity points, duplicates that force P + P in a bucket, P - P, r - 1, heavy buckets)."""
-    pk = keys32[0]
+def test_msm_adversarial_bucket_lists(ctx):
+    """Bucket lists that hit every exceptional branch of the accumulation and the segmented heavy-bucket path: infinity
+    points, one point repeated with the same scalar (P + P, then 2P + P ... in one bucket of every window), P and -P with
+    the same scalar (P - P), scalars r - 1 / 0 / 1, and an MSM whose every list is the whole input (all buckets heavy:
+    k_heavy_plan / k_bucket_heavy segments / k_heavy_combine)."""
     rng = random.Random(303)
-    PK = ob.ProvingKey(ctx, pk)
-    batch = 40
-    nul, sec, rec, sib, bits = rand_inputs(rng, batch, 32)
-    rs = cport.frs([rng.randrange(R) for _ in range(2 * batch)])
-    monkeypatch.setenv("OG_CHUNK", "32")
-    ref = ob.prove(PK, nul, sec, rec, sib, bits, rs)
-    for mode in ("1", "3"):
-        monkeypatch.setenv("OG_AFFINE", mode)
-        assert ob.prove(PK, nul, sec, rec, sib, bits, rs) == ref, mode
-    monkeypatch.setenv("OG_AFF_ROUNDS", "7")       # most lists are longer than 7: the serial tail of k_aff_finish
-    assert ob.prove(PK, nul, sec, rec, sib, bits, rs) == ref
-    monkeypatch.delenv("OG_AFF_ROUNDS"); monkeypatch.delenv("OG_AFFINE")
-    PK.close()
-    monkeypatch.setenv("OG_AFFINE_ONESHOT", "1")
     n = 3000
     pts = bytearray(rand_g1(rng, n))
     sc = [rng.randrange(R) for _ in range(n)]
@@ -404,25 +390,28 @@ def test_batched_affine_accumulation_matches_xyzz(ctx, keys32, monkeypatch):
     for i in range(300, 900):
         pts[64 * i:64 * i + 64] = pts[64 * 300:64 * 300 + 64]                 # one point 600 times ...
     for i in range(300, 600):
-        sc[i] = sc[300]                                                       # ... 300 of them with the same scalar: P + P chains
+        sc[i] = sc[300]                                                       # ... 300 of them with the same scalar
     neg = bn.g1_to_bytes(bn.g1_neg(bn.g1_from_bytes(bytes(pts[64 * 1000:64 * 1000 + 64]))))
     pts[64 * 1001:64 * 1001 + 64] = neg; sc[1001] = sc[1000]                  # P and -P with the same scalar: P - P
     sc[1500], sc[1501], sc[1502] = R - 1, 0, 1
-    for i in range(2000, 2064):                                               # 64 equal entries in one bucket of every window:
-        pts[64 * i:64 * i + 64] = pts[64 * 2000:64 * 2000 + 64]; sc[i] = sc[2000]    # P, P + P (doubling), 2P + P, ...
+    for i in range(2000, 2064):                                               # 64 equal entries in one bucket of every window
+        pts[64 * i:64 * i + 64] = pts[64 * 2000:64 * 2000 + 64]; sc[i] = sc[2000]
     pts, scb = bytes(pts), cport.frs(sc)
     assert ctx.msm_g1(pts, scb) == cport.g1_msm(pts, scb)
-    same = cport.frs([sc[7]] * n)                                             # every bucket list = the whole input: heavy buckets
+    same = cport.frs([sc[7]] * n)                                             # every bucket list = the whole input
     assert ctx.msm_g1(pts, same) == cport.g1_msm(pts, same)
     n2 = 700
     p2 = bytearray(rand_g2(rng, n2)); s2 = [rng.randrange(R) for _ in range(n2)]
-    for i in range(100, 200):
-        p2[128 * i:128 * i + 128] = p2[128 * 100:128 * 100 + 128]; s2[i] = s2[100]
+    for i in range(100, 400):
+        p2[128 * i:128 * i + 128] = p2[128 * 100:128 * 100 + 128]; s2[i] = s2[100]      # 300 equal entries: heavy in G2
     p2[128 * 5:128 * 5 + 128] = bytes(128)
     p2, s2b = bytes(p2), cport.frs(s2)
     assert ctx.msm_g2(p2, s2b) == cport.g2_msm(p2, s2b)
-    big = rand_g1(rng, 1 << 16); bsc = rand_fr_bytes(rng, 1 << 16)
-    assert ctx.msm_g1(big, bsc) == cport.g1_msm(big, bsc)
+    big = rand_g1(rng, 1 << 16)
+    wl = bytearray(rand_fr_bytes(rng, 1 << 16))
+    for i in range(0, 1 << 16, 2):
+        wl[32 * i:32 * i + 32] = (1).to_bytes(32, "little")                  # half the scalars are 1: one bucket of 32768 entries
+    assert ctx.msm_g1(big, bytes(wl)) == cport.g1_msm(big, bytes(wl))
 
 
 def test_external_known_answers(ctx):

@@ -94,6 +94,46 @@ def test_babyjubjub_verification_core_on_host(h):
     assert list(out.raw) == [1 if e else 0 for e in expect] + [2]
 
 
+def test_babyjubjub_signing_core_on_host(h):
+    """bjj_sign_one (key derivation + signing, mod.rs:206-237) compiled for the host against the oracle's restatement,
+    and its integer step s = (r + h a) mod ORDER on crafted operands -- including results in [r, ORDER), the case the
+    reference answers with Err("Invalid repr") and which random signatures reach with probability ~3 * 10^-39."""
+    from oracle import babyjubjub as bjj
+    rng = random.Random(17)
+    n = 6
+    sks = [rng.randrange(R) for _ in range(n - 2)] + [0, 1]
+    rnds = [rng.randrange(R) for _ in range(n)]
+    msgs = [rng.randrange(R) for _ in range(n - 1)] + [0]
+    fb = bn.fr_to_bytes
+    pkx, odd = C.create_string_buffer(32 * n), C.create_string_buffer(n)
+    sigs, st = C.create_string_buffer(96 * n), C.create_string_buffer(n)
+    h.ht_bjj_sign(b"".join(map(fb, sks)), b"".join(map(fb, rnds)), b"".join(map(fb, msgs)), n, fb(bjj.BASE[0]) + fb(bjj.BASE[1]), pkx, odd, sigs, st)
+    for i in range(n):
+        pk = bjj.to_pub(sks[i])
+        (rx, ry), s_ = bjj.sign(sks[i], rnds[i], msgs[i])
+        assert st.raw[i] == 1
+        assert pkx.raw[32 * i:32 * i + 32] == fb(pk[0]) and odd.raw[i] == pk[1]
+        assert sigs.raw[96 * i:96 * i + 96] == fb(rx) + fb(ry) + fb(s_)
+        assert bjj.verify(pk, msgs[i], ((rx, ry), s_))
+    O = bjj.ORDER
+    cases = [(rng.randrange(R), rng.randrange(R), rng.randrange(R)) for _ in range(200)]
+    cases += [(0, 0, 0), (R - 1, R - 1, R - 1), (O - 1 - 5 * 7 % O, 5, 7), (R, 0, 0) if False else (R - 1, 1, 1)]
+    # force results into [R, ORDER): s = target  <=  r = target - h*a mod ORDER (must itself be < R to be a field element)
+    forced = 0
+    while forced < 20:
+        hh, aa = rng.randrange(R), rng.randrange(R)
+        target = rng.randrange(R, O)
+        rr = (target - hh * aa) % O
+        if rr < R:
+            cases.append((rr, hh, aa)); forced += 1
+    le = lambda v: v.to_bytes(32, "little")
+    out = C.create_string_buffer(32 * len(cases))
+    h.ht_bjj_s_mod_order(b"".join(le(c[0]) for c in cases), b"".join(le(c[1]) for c in cases), b"".join(le(c[2]) for c in cases), out, len(cases))
+    got = [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(len(cases))]
+    assert got == [(r_ + h_ * a_) % O for r_, h_, a_ in cases]
+    assert sum(g >= R for g in got) >= 20
+
+
 def test_wide_products_and_separate_reduction(h):
     """mul_wide / sqr_wide / mont_reduce_wide (squarings and the lazy Fq2 product are built on them)."""
     rng = random.Random(6)
