@@ -118,12 +118,17 @@ int32_t og_mimc7_merkle_append(og_ctx* ctx, uint32_t depth, uint64_t start, cons
  * out_status[i]: 1 verifies, 0 does not, 2 = the reference would return Err (pk does not decompress). */
 int32_t og_bjj_verify_batch(og_ctx* ctx, const uint8_t* pk_x, const uint8_t* pk_is_odd, const uint8_t* messages,
                             const uint8_t* signatures, uint32_t n, int32_t hash_kind, uint8_t* out_status);
+int32_t og_bjj_verify_batch_dev(og_ctx* ctx, const uint8_t* d_pk_x, const uint8_t* d_pk_is_odd, const uint8_t* d_messages,
+                                const uint8_t* d_signatures, uint32_t n, int32_t hash_kind, uint8_t* d_out_status);
 /* Batch of PrivateKey::to_pub + PrivateKey::sign (mod.rs:206-237): per key 32 B secret scalar, 32 B randomness, 32 B message
  * -> compressed public key (x, is_odd), signature R.x || R.y || s.  out_status[i]: 1 = written; 2 = the reference returns
  * Err("Invalid repr") because s = (r + h a) mod ORDER does not fit the field (ORDER > r, mod.rs:222-233). */
 int32_t og_bjj_sign_batch(og_ctx* ctx, const uint8_t* secret_keys, const uint8_t* randomness, const uint8_t* messages,
                           uint32_t n, int32_t hash_kind, uint8_t* out_pk_x, uint8_t* out_pk_is_odd,
                           uint8_t* out_signatures, uint8_t* out_status);
+int32_t og_bjj_sign_batch_dev(og_ctx* ctx, const uint8_t* d_secret_keys, const uint8_t* d_randomness, const uint8_t* d_messages,
+                              uint32_t n, int32_t hash_kind, uint8_t* d_out_pk_x, uint8_t* d_out_pk_is_odd,
+                              uint8_t* d_out_signatures, uint8_t* d_out_status);
 
 /* ---- MSM (BASELINE configs 3 and 5) ----------------------------------------------------------- */
 int32_t og_msm_g1(og_ctx* ctx, const uint8_t* points, const uint8_t* scalars, uint64_t n, uint8_t* out64);

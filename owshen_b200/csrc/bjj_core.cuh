@@ -91,9 +91,38 @@ OG_HD bool fr_is_odd(const Fr& v) { uint32_t c[8]; v.to_canonical(c); return c[0
 
 // status: 1 verifies, 0 does not, 2 = Err in the reference (public key does not decompress).  `h_mimc` is only
 // read when hash_kind == 1 (the caller computes MultiMiMC7([R.x, R.y, pk.x, pk.y, msg]) after decompression via cb).
-template <class HashFn>
-OG_HD uint8_t bjj_verify_one(const Fr& x, bool pk_odd, const Fr& msg, const Fr& rx, const Fr& ry, const Fr& s, const Fr& base_x,
-                             const Fr& base_y, HashFn hash5) {
+// fixed-base multiplication k * BASE from a table of window multiples: tab[w * 15 + d - 1] = d * 16^w * BASE (affine x, y),
+// 64 additions instead of 256 doublings + ~128 additions; the additions are the reference's projective formulas
+OG_BJJ_FN void bjj_mul_base_table(BjjPoint* out, const Fr* tab_xy, const Fr* k, const Fr* A, const Fr* D) {
+    uint32_t s[8];
+    k->to_canonical(s);
+    BjjPoint acc{Fr::zero(), Fr::one(), Fr::zero()};
+    for (int w = 0; w < 64; w++) {
+        uint32_t d = (s[w >> 3] >> ((w & 7) * 4)) & 15;
+        if (!d) continue;
+        const Fr* e = tab_xy + 2 * (w * 15 + d - 1);
+        BjjPoint q{e[0], e[1], Fr::one()};
+        bjj_add(&acc, &q, A, D);
+    }
+    *out = acc;
+}
+
+// default fixed-base multiplier: plain double-and-add on BASE (host harness, and the table builder itself)
+struct BjjMulBasePlain {
+    Fr bx, by;
+    OG_HD void operator()(BjjPoint* out, const Fr* k, const Fr* A, const Fr* D) const {
+        BjjPoint base{bx, by, Fr::one()};
+        bjj_mul(out, &base, k, A, D);
+    }
+};
+struct BjjMulBaseTable {
+    const Fr* tab_xy;
+    OG_HD void operator()(BjjPoint* out, const Fr* k, const Fr* A, const Fr* D) const { bjj_mul_base_table(out, tab_xy, k, A, D); }
+};
+
+template <class HashFn, class MulBaseFn>
+OG_HD uint8_t bjj_verify_one(const Fr& x, bool pk_odd, const Fr& msg, const Fr& rx, const Fr& ry, const Fr& s, MulBaseFn mul_base,
+                             HashFn hash5) {
     const Fr A = bjj_a(), D = bjj_d(), one = Fr::one();
     // decompress (mod.rs:88-98)
     Fr xx = x.sqr();
@@ -106,8 +135,8 @@ OG_HD uint8_t bjj_verify_one(const Fr& x, bool pk_odd, const Fr& msg, const Fr& 
     if (!bjj_on_curve(x, y, A, D) || !bjj_on_curve(rx, ry, A, D)) return 0;
     Fr in[5] = {rx, ry, x, y, msg};
     Fr h = hash5(in);
-    BjjPoint base{base_x, base_y, one}, pk{x, y, one}, rr{rx, ry, one}, sb, ha;
-    bjj_mul(&sb, &base, &s, &A, &D);
+    BjjPoint pk{x, y, one}, rr{rx, ry, one}, sb, ha;
+    mul_base(&sb, &s, &A, &D);
     bjj_mul(&ha, &pk, &h, &A, &D);
     bjj_add(&ha, &rr, &A, &D);
     // affine equality by cross-multiplication; an empty accumulator is the affine point (0, 1)
@@ -162,18 +191,18 @@ OG_BJJ_FN void bjj_to_affine(Fr* x, Fr* y, const BjjPoint* p) {
 
 // PrivateKey::to_pub + sign (mod.rs:207-237).  status 1: pk and signature written; 2: the reference returns
 // Err("Invalid repr") because s >= r cannot be represented as an Fp (ORDER > r: the wart SURVEY.md 8a notes).
-template <class HashFn2, class HashFn5>
-OG_HD uint8_t bjj_sign_one(const Fr& sk, const Fr& randomness, const Fr& msg, const Fr& base_x, const Fr& base_y, HashFn2 hash2,
+template <class HashFn2, class HashFn5, class MulBaseFn>
+OG_HD uint8_t bjj_sign_one(const Fr& sk, const Fr& randomness, const Fr& msg, MulBaseFn mul_base, HashFn2 hash2,
                            HashFn5 hash5, Fr* pk_x, bool* pk_odd, Fr* sig_rx, Fr* sig_ry, Fr* sig_s) {
-    const Fr A = bjj_a(), D = bjj_d(), one = Fr::one();
-    BjjPoint base{base_x, base_y, one}, acc;
+    const Fr A = bjj_a(), D = bjj_d();
+    BjjPoint acc;
     Fr px, py, rx, ry;
-    bjj_mul(&acc, &base, &sk, &A, &D);               // to_pub: BASE * sk, compressed (x, parity of y); decompressing gives y back
+    mul_base(&acc, &sk, &A, &D);                       // to_pub: BASE * sk, compressed (x, parity of y); decompressing gives y back
     bjj_to_affine(&px, &py, &acc);
     *pk_x = px; *pk_odd = fr_is_odd(py);
     Fr in2[2] = {randomness, msg};
     Fr r = hash2(in2);                                 // r = H(b, M)
-    bjj_mul(&acc, &base, &r, &A, &D);                // R = r B
+    mul_base(&acc, &r, &A, &D);                        // R = r B
     bjj_to_affine(&rx, &ry, &acc);
     Fr in5[5] = {rx, ry, px, py, msg};
     Fr h = hash5(in5);                                 // h = H(R, A, M)

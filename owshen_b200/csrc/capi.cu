@@ -142,6 +142,7 @@ void og_free(og_ctx* ctx) {
     ntt_free_tables(ctx);
     if (ctx->g1_fixed) cudaFree(ctx->g1_fixed);
     if (ctx->g2_fixed) cudaFree(ctx->g2_fixed);
+    if (ctx->bjj_fixed) cudaFree(ctx->bjj_fixed);
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -604,6 +605,19 @@ int32_t og_bjj_verify_batch(og_ctx* ctx, const uint8_t* pk_x, const uint8_t* pk_
     return check_flag(ctx);
 }
 
+int32_t og_bjj_verify_batch_dev(og_ctx* ctx, const uint8_t* d_pk_x, const uint8_t* d_pk_is_odd, const uint8_t* d_messages,
+                                const uint8_t* d_signatures, uint32_t n, int32_t hash_kind, uint8_t* d_out_status) {
+    OG_ENTER(ctx);
+    if (!ctx || hash_kind < 0 || hash_kind > 1 || (n && (!d_pk_x || !d_pk_is_odd || !d_messages || !d_signatures || !d_out_status))) return OG_E_INVALID;
+    return bjj_verify_dev(ctx, d_pk_x, d_pk_is_odd, d_messages, d_signatures, n, hash_kind, d_out_status);
+}
+int32_t og_bjj_sign_batch_dev(og_ctx* ctx, const uint8_t* d_secret_keys, const uint8_t* d_randomness, const uint8_t* d_messages, uint32_t n,
+                              int32_t hash_kind, uint8_t* d_out_pk_x, uint8_t* d_out_pk_is_odd, uint8_t* d_out_signatures, uint8_t* d_out_status) {
+    OG_ENTER(ctx);
+    if (!ctx || hash_kind < 0 || hash_kind > 1 ||
+        (n && (!d_secret_keys || !d_randomness || !d_messages || !d_out_pk_x || !d_out_pk_is_odd || !d_out_signatures || !d_out_status))) return OG_E_INVALID;
+    return bjj_sign_dev(ctx, d_secret_keys, d_randomness, d_messages, n, hash_kind, d_out_pk_x, d_out_pk_is_odd, d_out_signatures, d_out_status);
+}
 int32_t og_bjj_sign_batch(og_ctx* ctx, const uint8_t* secret_keys, const uint8_t* randomness, const uint8_t* messages, uint32_t n,
                           int32_t hash_kind, uint8_t* out_pk_x, uint8_t* out_pk_is_odd, uint8_t* out_signatures, uint8_t* out_status) {
     OG_ENTER(ctx);

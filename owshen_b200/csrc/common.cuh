@@ -43,6 +43,7 @@ struct og_ctx {
     og::NttTables* ntt[32] = {nullptr};
     void* g1_fixed = nullptr;        // fixed-base tables of the generators (setup only)
     void* g2_fixed = nullptr;
+    void* bjj_fixed = nullptr;       // window multiples of the BabyJubJub BASE (bjj_impl.cuh)
     bool digits_smem_opt_in = false; // cudaFuncSetAttribute(k_digits_count_tiled) done for this device
 
     // optional per-kernel timing: CUDA events around every launch of this library (og_profile)

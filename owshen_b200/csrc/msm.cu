@@ -120,9 +120,10 @@ struct DigitIter {
     }
 };
 
-// one thread per scalar.  The scatter is pure memory latency (ncu, profiles/r2_ncu_digits.md: 93 % of the warp samples wait on
-// the atomic's round trip, issue slots 17 % busy), so the digits of EIGHT windows are cut first, their eight cursor atomics
-// issued back to back and only then the eight dependent 4-byte stores: eight round trips in flight per thread instead of one.
+// one thread per scalar, global atomics (one-shot MSMs: up to 2^15 buckets x 16 windows of keys).  The scatter is pure
+// atomic round-trip latency (ncu, profiles/r2_ncu_digits.md: 93 % of the warp samples on the long scoreboard, issue slots 17 %
+// busy); cutting eight windows first and issuing their eight atomics back to back was measured SLOWER (21.3 vs 20.1 ms per 1024
+// proofs, profiles/r2_small_ab.md): the L2 atomic units, not the per-thread dependency, are what the kernel waits for.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restrict__ counts, const uint32_t* __restrict__ offsets,
                                                 uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, int* flag) {
@@ -131,38 +132,15 @@ __global__ void __launch_bounds__(256) k_digits(DigitPlan P, uint32_t* __restric
     if (i >= P.n) return;
     DigitIter it;
     if (!it.load(P, prob, i, flag)) return;
-    const uint32_t c = P.c, half = 1u << (c - 1), mask = (1u << c) - 1;
-    const uint32_t key0 = prob * P.key_stride_problem;
-    uint32_t carry = 0;
-    for (uint32_t w0 = 0; w0 < P.n_windows; w0 += 8) {
-        uint32_t key[8], ent[8], pos[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const uint32_t w = w0 + q;
-            key[q] = 0xffffffffu;
-            if (w < P.n_windows) {
-                uint32_t bit = w * c, word = bit >> 5, sh = bit & 31;
-                uint64_t two = ((uint64_t)it.s[word + 1] << 32) | it.s[word];
-                uint32_t v = ((uint32_t)(two >> sh) & mask) + carry;
-                uint32_t neg = v > half;
-                uint32_t mag = neg ? (1u << c) - v : v;
-                carry = neg;
-                if (mag) {
-                    key[q] = (key0 + w * P.key_stride_window) * P.nb + mag - 1;
-                    ent[q] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
-                }
-            }
-        }
+    it.for_each(P, [&](uint32_t w, uint32_t b, uint32_t neg) {
+        uint32_t key = (prob * P.key_stride_problem + w * P.key_stride_window) * P.nb + b;
         if (!SCATTER) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) if (key[q] != 0xffffffffu) atomicAdd(&counts[key[q]], 1u);
+            atomicAdd(&counts[key], 1u);
         } else {
-#pragma unroll
-            for (int q = 0; q < 8; q++) if (key[q] != 0xffffffffu) pos[q] = atomicAdd(&cursor[key[q]], 1u);   // cursor starts at the bucket's offset (k_scan_apply)
-#pragma unroll
-            for (int q = 0; q < 8; q++) if (key[q] != 0xffffffffu) sorted[pos[q]] = ent[q];
+            uint32_t pos = atomicAdd(&cursor[key], 1u);          // cursor starts at the bucket's offset (k_scan_apply)
+            sorted[pos] = (((uint32_t)i + w * P.tidx_window_stride) << 1) | neg;
         }
-    }
+    });
 }
 
 // Tiled histogram for the batched prover (one group per proof, nb <= 32768): a CTA owns a tile of one problem's
@@ -560,8 +538,12 @@ template <> struct RedOps<Fq> {
 };
 #endif
 
-template <class F, bool HAS_U, int MINB>
-__global__ void __launch_bounds__(64, MINB) k_reduce_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
+// measured (profiles/r2_small_ab.md): G1 25.5 (registers, out-of-line ops) vs 29.6 ms (shared memory); G2 25.3 (registers, spilling) vs 24.1 ms
+template <class F> constexpr bool RED_SM_DEFAULT = sizeof(F) != 32;
+
+// (64 threads, 206 registers for G1: 4 resident CTAs per SM; asking ptxas for 6 or 8 costs spills: 26.4 / 27.6 vs 25.2 ms)
+template <class F, bool HAS_U>
+__global__ void __launch_bounds__(64) k_reduce_level(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
                                                      uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
                                                      uint32_t fan_log2, XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ U_out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -582,6 +564,100 @@ __global__ void __launch_bounds__(64, MINB) k_reduce_level(const XYZZ<F>* __rest
     }
     S_out[(size_t)g * n_out + p] = R;
     U_out[(size_t)g * n_out + p] = T;
+}
+
+// ---- the same level with the running sums R and T in shared memory -----------------------------------------------------
+// G2: R, T and one addend are 192 registers before a single temporary, so the register version spills 2.4-3 KB per thread
+// (706 LDL / 586 STL in its SASS).  Here R and T live in shared memory (16-byte chunks interleaved over the CTA's 64 threads:
+// conflict-free), addend coordinates are fetched where the formula uses them, and only the temporaries of ONE addition are
+// in registers.  Infinity is tracked in a flag per running sum instead of zz == 0.
+template <class F> struct RedSm {
+    static constexpr int CH = sizeof(F) / 16, THREADS = 64;
+    uint4* base;                                        // [2 sums][4 coordinates][CH chunks][64 threads]
+    __device__ __forceinline__ F ld(int acc, int coord) const {
+        F v; uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+        for (int c = 0; c < CH; c++) { uint4 q = base[((acc * 4 + coord) * CH + c) * THREADS]; w[4 * c] = q.x; w[4 * c + 1] = q.y; w[4 * c + 2] = q.z; w[4 * c + 3] = q.w; }
+        return v;
+    }
+    __device__ __forceinline__ void st(int acc, int coord, const F& v) const {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+        for (int c = 0; c < CH; c++) base[((acc * 4 + coord) * CH + c) * THREADS] = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+    }
+};
+template <class F> struct RedGlobalOp {                 // addend in global memory
+    const XYZZ<F>* p;
+    __device__ __forceinline__ bool inf() const { return p->zz.is_zero(); }
+    __device__ __forceinline__ F coord(int c) const { return c == 0 ? p->x : (c == 1 ? p->y : (c == 2 ? p->zz : p->zzz)); }
+};
+template <class F> struct RedSmOp {                     // addend = the other running sum
+    RedSm<F> M; int acc; bool is_inf;
+    __device__ __forceinline__ bool inf() const { return is_inf; }
+    __device__ __forceinline__ F coord(int c) const { return M.ld(acc, c); }
+};
+
+template <class F, class Op>
+__device__ __forceinline__ void red_sm_add(const RedSm<F>& M, int a, bool& a_inf, const Op& o) {
+    if (o.inf()) return;
+    if (a_inf) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) M.st(a, c, o.coord(c));
+        a_inf = false;
+        return;
+    }
+    F u1 = M.ld(a, 0) * o.coord(2);
+    F p = o.coord(0) * M.ld(a, 2) - u1;
+    F s1 = M.ld(a, 1) * o.coord(3);
+    F r = o.coord(1) * M.ld(a, 3) - s1;
+    if (p.is_zero()) {
+        if (r.is_zero()) {                              // equal points: double through registers (rare)
+            XYZZ<F> t{M.ld(a, 0), M.ld(a, 1), M.ld(a, 2), M.ld(a, 3)};
+            t = t.dbl();
+            M.st(a, 0, t.x); M.st(a, 1, t.y); M.st(a, 2, t.zz); M.st(a, 3, t.zzz);
+        } else {
+            a_inf = true;
+        }
+        return;
+    }
+    F pp = p.sqr();
+    F ppp = p * pp;
+    F q1 = u1 * pp;
+    F x3 = r.sqr() - ppp - q1.dbl();
+    M.st(a, 0, x3);
+    M.st(a, 1, r * (q1 - x3) - s1 * ppp);
+    M.st(a, 2, M.ld(a, 2) * o.coord(2) * pp);
+    M.st(a, 3, M.ld(a, 3) * o.coord(3) * ppp);
+}
+
+template <class F, bool HAS_U>
+__global__ void __launch_bounds__(64) k_reduce_level_sm(const XYZZ<F>* __restrict__ S_in, const XYZZ<F>* __restrict__ U_in,
+                                                        uint32_t n_in, uint32_t n_out, uint32_t n_groups, uint32_t w_log2,
+                                                        uint32_t fan_log2, XYZZ<F>* __restrict__ S_out, XYZZ<F>* __restrict__ U_out) {
+    __shared__ uint4 red_sm[2 * 4 * RedSm<F>::CH * 64];
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_groups * n_out) return;
+    uint32_t g = t / n_out, p = t % n_out;
+    const XYZZ<F>* S = S_in + (size_t)g * n_in;
+    uint32_t lo = p << fan_log2, hi = min(n_in, lo + (1u << fan_log2));
+    RedSm<F> M{red_sm + threadIdx.x};
+    bool r_inf = true, t_inf = true;
+    for (uint32_t i = hi - 1; i > lo; i--) {
+        red_sm_add(M, 0, r_inf, RedGlobalOp<F>{S + i});
+        red_sm_add(M, 1, t_inf, RedSmOp<F>{M, 0, r_inf});
+    }
+    red_sm_add(M, 0, r_inf, RedGlobalOp<F>{S + lo});
+    if (w_log2 && !t_inf) {
+        XYZZ<F> tt{M.ld(1, 0), M.ld(1, 1), M.ld(1, 2), M.ld(1, 3)};
+        for (uint32_t k = 0; k < w_log2; k++) tt = tt.dbl();
+        M.st(1, 0, tt.x); M.st(1, 1, tt.y); M.st(1, 2, tt.zz); M.st(1, 3, tt.zzz);
+    }
+    if (HAS_U) {
+        const XYZZ<F>* U = U_in + (size_t)g * n_in;
+        for (uint32_t i = lo; i < hi; i++) red_sm_add(M, 1, t_inf, RedGlobalOp<F>{U + i});
+    }
+    S_out[(size_t)g * n_out + p] = r_inf ? XYZZ<F>::inf() : XYZZ<F>{M.ld(0, 0), M.ld(0, 1), M.ld(0, 2), M.ld(0, 3)};
+    U_out[(size_t)g * n_out + p] = t_inf ? XYZZ<F>::inf() : XYZZ<F>{M.ld(1, 0), M.ld(1, 1), M.ld(1, 2), M.ld(1, 3)};
 }
 
 // total_g = U_g + S_g   (weights are b+1)
@@ -656,13 +732,16 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
         uint32_t n_out = (n_in + (1u << fan_log2) - 1) >> fan_log2;
         uint32_t threads = n_groups * n_out;
         const char* rn = sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2";
-        // resident 64-thread CTAs per SM asked of ptxas (G1: 4 = 206 registers, 6 = 168, 8 = 128 with spills): OG_RED_OCC
-        static const int rocc = [] { const char* v = getenv("OG_RED_OCC"); return v ? atoi(v) : 0; }();
-#define OG_RED_LAUNCH(HASU, MB) { auto k = k_reduce_level<F, HASU, MB>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
-        if (sizeof(F) == 32 && rocc == 6) { if (U_in) OG_RED_LAUNCH(true, 6) else OG_RED_LAUNCH(false, 6) }
-        else if (sizeof(F) == 32 && rocc == 8) { if (U_in) OG_RED_LAUNCH(true, 8) else OG_RED_LAUNCH(false, 8) }
-        else { if (U_in) OG_RED_LAUNCH(true, 1) else OG_RED_LAUNCH(false, 1) }
-#undef OG_RED_LAUNCH
+        // OG_RED_SM: bit 0 = shared-memory running sums for G1, bit 1 = for G2 (A/B, profiles/r2_small_ab.md)
+        static const int red_sm = [] { const char* v = getenv("OG_RED_SM"); return v ? atoi(v) : -1; }();
+        const bool use_sm = red_sm >= 0 ? ((red_sm >> (sizeof(F) == 32 ? 0 : 1)) & 1) != 0 : RED_SM_DEFAULT<F>;
+        if (use_sm) {
+            if (U_in) { auto k = k_reduce_level_sm<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+            else { auto k = k_reduce_level_sm<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+        } else {
+            if (U_in) { auto k = k_reduce_level<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+            else { auto k = k_reduce_level<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
+        }
         S_in = bufS[pp]; U_in = bufU[pp];
         pp ^= 1;
         n_in = n_out;

@@ -120,12 +120,17 @@ def main():
             scd = dev(sc, device)
             torch.cuda.synchronize()
             ms = timed(ctx, lambda: check(fn_(ctx._h, pts.data_ptr(), scd.data_ptr(), n, outp.data_ptr())), args.warmup, args.reps)
+            ctx.profile(True)
+            check(fn_(ctx._h, pts.data_ptr(), scd.data_ptr(), n, outp.data_ptr()))
+            prof = ctx.profile_dump()
+            ctx.profile(False)
             per_pair = 96 if curve == "g1" else 160
             c = min(16, max(2, log_n - 3)); windows = (255 + c - 1) // c
             madds = n * windows if kind == "uniform" else None
             muls = (madds * (10 if curve == "g1" else 28)) if madds else 0
             line(f"msm_{curve}_2^{log_n}_{kind} (config 3)", ms, per_pair * n, muls,
                  {"points_per_s": n / (ms * 1e-3), "window_bits": c, "windows": windows,
+                  "kernels_ms_one_run": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]},
                   "l2": "sorted digit lists + buckets (> 126 MB) stream through L2 every repetition"})
 
     # ---- NTT ------------------------------------------------------------------------------------
@@ -138,16 +143,25 @@ def main():
                    flush if n * batch * 32 < (200 << 20) else None)
         line(f"ntt_2^{log_n}_x{batch} (bytes in/out incl. Montgomery conversion kernels)", ms, 64 * n * batch, int(n * batch * (log_n / 2 + 2 - 0.75)),
              {"elements_per_s": n * batch / (ms * 1e-3), "note": "products counted: n/2*log n butterflies - 0.75 n skipped unit twiddles + 2 n boundary conversions"})
-    # ---- BabyJubJub batch verification --------------------------------------------
+    # ---- BabyJubJub batch signing and verification: device-resident, CUDA-event timed -------------------
     n = 1 << 16
-    rb = rng.randbytes
-    pkx = fr_bytes(rng, n); odd = bytes(n); msg = fr_bytes(rng, n); sg = fr_bytes(rng, 3 * n)
-    import time
-    ctx.bjj_verify_batch(pkx[:32 * 64], odd[:64], msg[:32 * 64], sg[:96 * 64])
-    t0 = time.perf_counter(); st = ctx.bjj_verify_batch(pkx, odd, msg, sg); dt = time.perf_counter() - t0
-    print(json.dumps({"kernel": "bjj_verify_batch_65536 (random inputs: ~half fail at decompress, the rest run both scalar multiplications)",
-                      "ms_host_wall_incl_copies": dt * 1e3, "signatures_per_s": n / dt,
-                      "status_histogram": {str(k): st.count(bytes([k])) for k in (0, 1, 2)}}), flush=True)
+    sk, rnd, msg = (dev(fr_bytes(rng, n), device) for _ in range(3))
+    pkx = torch.empty(32 * n, dtype=torch.uint8, device=device); odd = torch.empty(n, dtype=torch.uint8, device=device)
+    sg = torch.empty(96 * n, dtype=torch.uint8, device=device); st = torch.empty(n, dtype=torch.uint8, device=device)
+    torch.cuda.synchronize()
+    for hk in (0, 1):
+        ms = timed(ctx, lambda: check(L.og_bjj_sign_batch_dev(ctx._h, sk.data_ptr(), rnd.data_ptr(), msg.data_ptr(), n, hk, pkx.data_ptr(), odd.data_ptr(),
+                                                             sg.data_ptr(), st.data_ptr())), args.warmup, args.reps)
+        # 2 fixed-base multiplications through the window table (64 additions x ~14 products) + 2 inversions (~380) + the hash
+        muls = n * (2 * 64 * 14 + 2 * 380 + (7 * 364 if hk else 5))
+        line(f"bjj_sign_batch_65536 hash_kind={hk} (to_pub + sign, mod.rs:206-237)", ms, n * (96 + 32 + 1 + 96 + 1), muls,
+             {"signatures_per_s": n / (ms * 1e-3), "signed": int((st == 1).sum().item())})
+        ms = timed(ctx, lambda: check(L.og_bjj_verify_batch_dev(ctx._h, pkx.data_ptr(), odd.data_ptr(), msg.data_ptr(), sg.data_ptr(), n, hk, st.data_ptr())),
+                   args.warmup, args.reps)
+        # decompress (one inversion + a square root: ~4 x 380 products) + h * A (256 doublings x 8 + ~128 additions x 14) + s * BASE (table)
+        muls = n * (4 * 380 + 256 * 8 + 128 * 14 + 64 * 14 + (5 * 364 if hk else 4))
+        line(f"bjj_verify_batch_65536 hash_kind={hk} (valid signatures from the line above)", ms, n * (32 + 1 + 32 + 96 + 1), muls,
+             {"signatures_per_s": n / (ms * 1e-3), "verified": int((st == 1).sum().item())})
     ctx.close()
 
 

@@ -55,13 +55,14 @@ void ht_g2_sum(const uint8_t* pts, uint64_t n, int mode, uint8_t* out) {
 }
 
 // ---- BabyJubJub verification core (bjj_core.cuh) on the host, placeholder-product hash -------------------
+#include <vector>
 #include "bjj_core.cuh"
 extern "C" void ht_bjj_verify(const uint8_t* pk_x, const uint8_t* pk_odd, const uint8_t* msgs, const uint8_t* sigs, uint32_t n,
                               const uint8_t* base_xy, uint8_t* out) {
     Fr bx = load<Fr>(base_xy), by = load<Fr>(base_xy + 32);
     for (uint32_t i = 0; i < n; i++) {
         out[i] = bjj_verify_one(load<Fr>(pk_x + 32 * i), pk_odd[i] != 0, load<Fr>(msgs + 32 * i), load<Fr>(sigs + 96 * i),
-                                load<Fr>(sigs + 96 * i + 32), load<Fr>(sigs + 96 * i + 64), bx, by,
+                                load<Fr>(sigs + 96 * i + 32), load<Fr>(sigs + 96 * i + 64), BjjMulBasePlain{bx, by},
                                 [](const Fr* in) { return in[0] * in[1] * in[2] * in[3] * in[4]; });
     }
 }
@@ -73,12 +74,38 @@ extern "C" void ht_bjj_sign(const uint8_t* sks, const uint8_t* rnds, const uint8
     for (uint32_t i = 0; i < n; i++) {
         Fr px, rx, ry, s;
         bool odd;
-        status[i] = bjj_sign_one(load<Fr>(sks + 32 * i), load<Fr>(rnds + 32 * i), load<Fr>(msgs + 32 * i), bx, by,
+        status[i] = bjj_sign_one(load<Fr>(sks + 32 * i), load<Fr>(rnds + 32 * i), load<Fr>(msgs + 32 * i), BjjMulBasePlain{bx, by},
                                  [](const Fr* in) { return in[0] * in[1]; },
                                  [](const Fr* in) { return in[0] * in[1] * in[2] * in[3] * in[4]; }, &px, &odd, &rx, &ry, &s);
         store(pk_x + 32 * i, px); pk_odd[i] = odd ? 1 : 0;
         store(sigs + 96 * i, rx); store(sigs + 96 * i + 32, ry); store(sigs + 96 * i + 64, s);
     }
+}
+// k * BASE through the window table (built here with the plain multiplier) against plain double-and-add; 1 = all equal
+extern "C" int ht_bjj_table_mul_matches(const uint8_t* ks, uint32_t n, const uint8_t* base_xy) {
+    const Fr A = bjj_a(), D = bjj_d();
+    Fr bx = load<Fr>(base_xy), by = load<Fr>(base_xy + 32);
+    std::vector<Fr> tab(2 * 64 * 15);
+    BjjPoint b{bx, by, Fr::one()};
+    for (int w = 0; w < 64; w++) {
+        Fr x, y;
+        bjj_to_affine(&x, &y, &b);
+        BjjPoint base{x, y, Fr::one()}, acc{Fr::zero(), Fr::one(), Fr::zero()};
+        for (int d = 1; d < 16; d++) {
+            bjj_add(&acc, &base, &A, &D);
+            bjj_to_affine(&tab[2 * (w * 15 + d - 1)], &tab[2 * (w * 15 + d - 1) + 1], &acc);
+        }
+        for (int k = 0; k < 4; k++) bjj_double(&b, &A);
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        Fr k = load<Fr>(ks + 32 * i), x1, y1, x2, y2;
+        BjjPoint p1, p2;
+        BjjMulBasePlain{bx, by}(&p1, &k, &A, &D);
+        BjjMulBaseTable{tab.data()}(&p2, &k, &A, &D);
+        bjj_to_affine(&x1, &y1, &p1); bjj_to_affine(&x2, &y2, &p2);
+        if (x1 != x2 || y1 != y2) return 0;
+    }
+    return 1;
 }
 extern "C" void ht_bjj_s_mod_order(const uint8_t* r, const uint8_t* h, const uint8_t* a, uint8_t* out, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) {

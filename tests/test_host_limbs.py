@@ -115,6 +115,8 @@ def test_babyjubjub_signing_core_on_host(h):
         assert pkx.raw[32 * i:32 * i + 32] == fb(pk[0]) and odd.raw[i] == pk[1]
         assert sigs.raw[96 * i:96 * i + 96] == fb(rx) + fb(ry) + fb(s_)
         assert bjj.verify(pk, msgs[i], ((rx, ry), s_))
+    ks = [rng.randrange(R) for _ in range(20)] + [0, 1, 15, 16, R - 1, 1 << 252]
+    assert h.ht_bjj_table_mul_matches(b"".join(map(fb, ks)), len(ks), fb(bjj.BASE[0]) + fb(bjj.BASE[1])) == 1     # window-table k * BASE
     O = bjj.ORDER
     cases = [(rng.randrange(R), rng.randrange(R), rng.randrange(R)) for _ in range(200)]
     cases += [(0, 0, 0), (R - 1, R - 1, R - 1), (O - 1 - 5 * 7 % O, 5, 7), (R, 0, 0) if False else (R - 1, 1, 1)]
