@@ -107,21 +107,16 @@ OG_BJJ_FN void bjj_mul_base_table(BjjPoint* out, const Fr* tab_xy, const Fr* k, 
     *out = acc;
 }
 
-// default fixed-base multiplier: plain double-and-add on BASE (host harness, and the table builder itself)
-struct BjjMulBasePlain {
-    Fr bx, by;
-    OG_HD void operator()(BjjPoint* out, const Fr* k, const Fr* A, const Fr* D) const {
-        BjjPoint base{bx, by, Fr::one()};
-        bjj_mul(out, &base, k, A, D);
-    }
-};
-struct BjjMulBaseTable {
-    const Fr* tab_xy;
-    OG_HD void operator()(BjjPoint* out, const Fr* k, const Fr* A, const Fr* D) const { bjj_mul_base_table(out, tab_xy, k, A, D); }
-};
+// the fixed base: its coordinates and, when available, the window table (nullptr = plain double-and-add: host harness)
+struct BjjBase { Fr x, y; const Fr* tab_xy; };
+OG_BJJ_FN void bjj_mul_base(BjjPoint* out, const BjjBase* b, const Fr* k, const Fr* A, const Fr* D) {
+    if (b->tab_xy) { bjj_mul_base_table(out, b->tab_xy, k, A, D); return; }
+    BjjPoint base{b->x, b->y, Fr::one()};
+    bjj_mul(out, &base, k, A, D);
+}
 
-template <class HashFn, class MulBaseFn>
-OG_HD uint8_t bjj_verify_one(const Fr& x, bool pk_odd, const Fr& msg, const Fr& rx, const Fr& ry, const Fr& s, MulBaseFn mul_base,
+template <class HashFn>
+OG_HD uint8_t bjj_verify_one(const Fr& x, bool pk_odd, const Fr& msg, const Fr& rx, const Fr& ry, const Fr& s, const BjjBase& base,
                              HashFn hash5) {
     const Fr A = bjj_a(), D = bjj_d(), one = Fr::one();
     // decompress (mod.rs:88-98)
@@ -136,7 +131,7 @@ OG_HD uint8_t bjj_verify_one(const Fr& x, bool pk_odd, const Fr& msg, const Fr& 
     Fr in[5] = {rx, ry, x, y, msg};
     Fr h = hash5(in);
     BjjPoint pk{x, y, one}, rr{rx, ry, one}, sb, ha;
-    mul_base(&sb, &s, &A, &D);
+    bjj_mul_base(&sb, &base, &s, &A, &D);
     bjj_mul(&ha, &pk, &h, &A, &D);
     bjj_add(&ha, &rr, &A, &D);
     // affine equality by cross-multiplication; an empty accumulator is the affine point (0, 1)
@@ -191,18 +186,18 @@ OG_BJJ_FN void bjj_to_affine(Fr* x, Fr* y, const BjjPoint* p) {
 
 // PrivateKey::to_pub + sign (mod.rs:207-237).  status 1: pk and signature written; 2: the reference returns
 // Err("Invalid repr") because s >= r cannot be represented as an Fp (ORDER > r: the wart SURVEY.md 8a notes).
-template <class HashFn2, class HashFn5, class MulBaseFn>
-OG_HD uint8_t bjj_sign_one(const Fr& sk, const Fr& randomness, const Fr& msg, MulBaseFn mul_base, HashFn2 hash2,
+template <class HashFn2, class HashFn5>
+OG_HD uint8_t bjj_sign_one(const Fr& sk, const Fr& randomness, const Fr& msg, const BjjBase& base, HashFn2 hash2,
                            HashFn5 hash5, Fr* pk_x, bool* pk_odd, Fr* sig_rx, Fr* sig_ry, Fr* sig_s) {
     const Fr A = bjj_a(), D = bjj_d();
     BjjPoint acc;
     Fr px, py, rx, ry;
-    mul_base(&acc, &sk, &A, &D);                       // to_pub: BASE * sk, compressed (x, parity of y); decompressing gives y back
+    bjj_mul_base(&acc, &base, &sk, &A, &D);                    // to_pub: BASE * sk, compressed (x, parity of y); decompressing gives y back
     bjj_to_affine(&px, &py, &acc);
     *pk_x = px; *pk_odd = fr_is_odd(py);
     Fr in2[2] = {randomness, msg};
     Fr r = hash2(in2);                                 // r = H(b, M)
-    mul_base(&acc, &r, &A, &D);                        // R = r B
+    bjj_mul_base(&acc, &base, &r, &A, &D);                    // R = r B
     bjj_to_affine(&rx, &ry, &acc);
     Fr in5[5] = {rx, ry, px, py, msg};
     Fr h = hash5(in5);                                 // h = H(R, A, M)

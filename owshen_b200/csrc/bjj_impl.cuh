@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(64) k_bjj_verify(const Fr* __restrict__ base_t
     Fr msg = load_canonical<Fr>(msgs + 32ull * i, flag);
     Fr rx = load_canonical<Fr>(sigs + 96ull * i, flag), ry = load_canonical<Fr>(sigs + 96ull * i + 32, flag);
     Fr s = load_canonical<Fr>(sigs + 96ull * i + 64, flag);
-    out[i] = bjj_verify_one(x, pk_odd[i] != 0, msg, rx, ry, s, BjjMulBaseTable{base_tab}, [hash_kind](const Fr* in) {
+    out[i] = bjj_verify_one(x, pk_odd[i] != 0, msg, rx, ry, s, BjjBase{Fr::zero(), Fr::zero(), base_tab}, [hash_kind](const Fr* in) {
         if (hash_kind == 0) return in[0] * in[1] * in[2] * in[3] * in[4];     // placeholder product, mod.rs:202-204
         return mimc7_multi_hash5(in);
     });
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(64) k_bjj_sign(const Fr* __restrict__ base_tab
     Fr sk = load_canonical<Fr>(sks + 32ull * i, flag), rnd = load_canonical<Fr>(rnds + 32ull * i, flag), msg = load_canonical<Fr>(msgs + 32ull * i, flag);
     Fr px, rx, ry, s;
     bool odd;
-    uint8_t st = bjj_sign_one(sk, rnd, msg, BjjMulBaseTable{base_tab},
+    uint8_t st = bjj_sign_one(sk, rnd, msg, BjjBase{Fr::zero(), Fr::zero(), base_tab},
         [hash_kind](const Fr* in) { return hash_kind == 0 ? in[0] * in[1] : mimc7_multi_hash_n(in, 2); },
         [hash_kind](const Fr* in) { return hash_kind == 0 ? in[0] * in[1] * in[2] * in[3] * in[4] : mimc7_multi_hash_n(in, 5); },
         &px, &odd, &rx, &ry, &s);

@@ -348,14 +348,15 @@ __global__ void __launch_bounds__(128, 8) k_bucket_acc_sm1(const Affine<Fq>* __r
             else inf = true;
             continue;
         }
+        // ordered so that few temporaries are live at a time: zz and zzz are updated as soon as pp / ppp exist
         Fq pp = p.sqr();
+        A.st(2, A.ld(2) * pp);
         Fq ppp = p * pp;
+        A.st(3, A.ld(3) * ppp);
         Fq q1 = A.ld(0) * pp;
         Fq x3 = r.sqr() - ppp - q1.dbl();
         A.st(0, x3);
         A.st(1, r * (q1 - x3) - A.ld(1) * ppp);
-        A.st(2, A.ld(2) * pp);
-        A.st(3, A.ld(3) * ppp);
     }
     buckets[key] = inf ? XYZZ<Fq>::inf() : XYZZ<Fq>{A.ld(0), A.ld(1), A.ld(2), A.ld(3)};
 }
@@ -413,14 +414,17 @@ __global__ void __launch_bounds__(128, 6) k_bucket_acc_sm(const Affine<Fq2>* __r
             else inf = true;
             continue;
         }
+        // ordered so that few Fq2 temporaries are live across the out-of-line multiplier calls (each one is 16 registers
+        // that would otherwise be spilled around every call): zz and zzz are updated as soon as pp / ppp exist
         Fq2 pp = p.sqr();
+        A.st(2, A.ld(2) * pp);
         Fq2 ppp = p * pp;
+        A.st(3, A.ld(3) * ppp);
         Fq2 q1 = A.ld(0) * pp;
         Fq2 x3 = r.sqr() - ppp - q1.dbl();
         A.st(0, x3);
-        A.st(1, r * (q1 - x3) - A.ld(1) * ppp);
-        A.st(2, A.ld(2) * pp);
-        A.st(3, A.ld(3) * ppp);
+        Fq2 t = A.ld(1) * ppp;
+        A.st(1, r * (q1 - x3) - t);
     }
     buckets[key] = inf ? XYZZ<Fq2>::inf() : XYZZ<Fq2>{A.ld(0), A.ld(1), A.ld(2), A.ld(3)};
 }
@@ -779,19 +783,71 @@ size_t msm_aff_scratch_bytes_g2(uint64_t) { return 0; }
 
 
 // ---- 6: one-shot MSM = Horner over the window totals ------------------------------------------------------
+// sum_w 2^(c w) T_w needs c (W - 1) ~ 240 SEQUENTIAL doublings whatever the order, and one thread's multiplier issues a
+// product every ~630 cycles, so round 1's single-thread Horner cost 0.7 ms (G1) / 2.2 ms (G2) of every one-shot MSM.
+// The nine products of an XYZZ doubling form three dependency levels of (2, 4, 3) independent products; four warps -- which
+// sit on the SM's four schedulers -- take one product each per level and meet at barriers:
+//   level 1: v = (2y)^2, xx = x^2     level 2: w = 2y v, s = x v, mm = (3xx)^2, zz' = v zz
+//   level 3: m (s - x3), w y, zzz' = w zzz   with x3 = mm - 2s, y3 = m (s - x3) - w y
 template <class F>
-__global__ void k_horner(const XYZZ<F>* __restrict__ totals, uint32_t n_windows, uint32_t c, uint8_t* __restrict__ out) {
-    if (blockIdx.x || threadIdx.x) return;
-    XYZZ<F> acc = XYZZ<F>::inf();
+__global__ void __launch_bounds__(128) k_horner(const XYZZ<F>* __restrict__ totals, uint32_t n_windows, uint32_t c, uint8_t* __restrict__ out) {
+    __shared__ XYZZ<F> acc;
+    __shared__ F l1[2], l2[4], l3[3];
+    __shared__ int acc_inf;
+    const int warp = threadIdx.x >> 5;
+    const bool lead = (threadIdx.x & 31) == 0;
+    if (threadIdx.x == 0) { acc = XYZZ<F>::inf(); acc_inf = 1; }
+    __syncthreads();
     for (int w = (int)n_windows - 1; w >= 0; w--) {
-        for (uint32_t k = 0; k < c; k++) xyzz_dbl_ni(&acc);
-        xyzz_add_ni(&acc, &totals[w]);
+        if (!acc_inf) {                                   // uniform: acc_inf is shared and only changes behind a barrier
+            for (uint32_t k = 0; k < c; k++) {
+                if (lead) {
+                    if (warp == 0) { F u = acc.y.dbl(); l1[0] = u.sqr(); }
+                    else if (warp == 1) l1[1] = acc.x.sqr();
+                }
+                __syncthreads();
+                if (lead) {
+                    F v = l1[0];
+                    if (warp == 0) { F u = acc.y.dbl(); l2[0] = u * v; }
+                    else if (warp == 1) l2[1] = acc.x * v;
+                    else if (warp == 2) { F xx = l1[1]; F m = xx.dbl() + xx; l2[2] = m.sqr(); }
+                    else l2[3] = v * acc.zz;
+                }
+                __syncthreads();
+                if (lead) {
+                    F s = l2[1];
+                    F x3 = l2[2] - s.dbl();
+                    if (warp == 0) { F xx = l1[1]; F m = xx.dbl() + xx; l3[0] = m * (s - x3); }
+                    else if (warp == 1) l3[1] = l2[0] * acc.y;
+                    else if (warp == 2) l3[2] = l2[0] * acc.zzz;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    F s = l2[1];
+                    acc.x = l2[2] - s.dbl();
+                    acc.y = l3[0] - l3[1];
+                    acc.zz = l2[3];
+                    acc.zzz = l3[2];
+                }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0) {
+            XYZZ<F> a = acc;
+            xyzz_add_ni(&a, &totals[w]);
+            acc = a;
+            acc_inf = a.is_inf() ? 1 : 0;
+        }
+        __syncthreads();
     }
-    Affine<F> a;
-    xyzz_to_affine_ni(&a, &acc);
-    constexpr int B = FieldIO<F>::BYTES;
-    FieldIO<F>::store(out, a.x);
-    FieldIO<F>::store(out + B, a.y);
+    if (threadIdx.x == 0) {
+        XYZZ<F> a = acc;
+        Affine<F> r;
+        xyzz_to_affine_ni(&r, &a);
+        constexpr int B = FieldIO<F>::BYTES;
+        FieldIO<F>::store(out, r.x);
+        FieldIO<F>::store(out + B, r.y);
+    }
 }
 
 static uint32_t pick_window(uint64_t n) {
@@ -836,7 +892,7 @@ static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sc
     }
 #endif
     OG_TRY((msm_buckets<F>(ctx, pts, sorted, offsets, counts, W, nb, n * W, buckets, lvl, heavy, cursor, totals, aff)));
-    OG_LAUNCH(ctx, k_horner<F>, 1, 32, 0, totals, W, c, d_out);
+    OG_LAUNCH(ctx, k_horner<F>, 1, 128, 0, totals, W, c, d_out);
     return OG_OK;
 }
 

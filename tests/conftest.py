@@ -13,12 +13,14 @@ def pytest_configure(config):
 
 
 def _cuda_device_present() -> bool:
-    """True iff the product library loads and finds a CUDA device (og_init succeeds on device 0)."""
-    try:
-        import owshen_b200 as ob
-        c = ob.Context(0)
-        c.close()
+    """True iff this host has an NVIDIA GPU at all (device node or a CUDA-capable torch).  Deliberately NOT "the product
+    library initialises": on a GPU box a library that fails to load or to find its symbols must make the gpu tests FAIL,
+    not skip (round 2 saw 27 silent skips caused by a stale .so before this was tightened)."""
+    if os.path.exists("/dev/nvidia0") or os.path.exists("/dev/nvidiactl"):
         return True
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
     except Exception:
         return False
 
@@ -37,9 +39,8 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def ctx():
     import owshen_b200 as ob
-    try:
-        c = ob.Context(0)
-    except (OSError, ob.OwshenB200Error) as e:
-        pytest.skip(f"no CUDA device: {e}")
+    if not _cuda_device_present():
+        pytest.skip("no CUDA device (libowshen_b200.so has no CPU path)")
+    c = ob.Context(0)          # on a GPU box a library that does not load or initialise is a failure, not a skip
     yield c
     c.close()

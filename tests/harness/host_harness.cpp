@@ -62,7 +62,7 @@ extern "C" void ht_bjj_verify(const uint8_t* pk_x, const uint8_t* pk_odd, const 
     Fr bx = load<Fr>(base_xy), by = load<Fr>(base_xy + 32);
     for (uint32_t i = 0; i < n; i++) {
         out[i] = bjj_verify_one(load<Fr>(pk_x + 32 * i), pk_odd[i] != 0, load<Fr>(msgs + 32 * i), load<Fr>(sigs + 96 * i),
-                                load<Fr>(sigs + 96 * i + 32), load<Fr>(sigs + 96 * i + 64), BjjMulBasePlain{bx, by},
+                                load<Fr>(sigs + 96 * i + 32), load<Fr>(sigs + 96 * i + 64), BjjBase{bx, by, nullptr},
                                 [](const Fr* in) { return in[0] * in[1] * in[2] * in[3] * in[4]; });
     }
 }
@@ -74,7 +74,7 @@ extern "C" void ht_bjj_sign(const uint8_t* sks, const uint8_t* rnds, const uint8
     for (uint32_t i = 0; i < n; i++) {
         Fr px, rx, ry, s;
         bool odd;
-        status[i] = bjj_sign_one(load<Fr>(sks + 32 * i), load<Fr>(rnds + 32 * i), load<Fr>(msgs + 32 * i), BjjMulBasePlain{bx, by},
+        status[i] = bjj_sign_one(load<Fr>(sks + 32 * i), load<Fr>(rnds + 32 * i), load<Fr>(msgs + 32 * i), BjjBase{bx, by, nullptr},
                                  [](const Fr* in) { return in[0] * in[1]; },
                                  [](const Fr* in) { return in[0] * in[1] * in[2] * in[3] * in[4]; }, &px, &odd, &rx, &ry, &s);
         store(pk_x + 32 * i, px); pk_odd[i] = odd ? 1 : 0;
@@ -100,8 +100,9 @@ extern "C" int ht_bjj_table_mul_matches(const uint8_t* ks, uint32_t n, const uin
     for (uint32_t i = 0; i < n; i++) {
         Fr k = load<Fr>(ks + 32 * i), x1, y1, x2, y2;
         BjjPoint p1, p2;
-        BjjMulBasePlain{bx, by}(&p1, &k, &A, &D);
-        BjjMulBaseTable{tab.data()}(&p2, &k, &A, &D);
+        BjjBase plain{bx, by, nullptr}, table{bx, by, tab.data()};
+        bjj_mul_base(&p1, &plain, &k, &A, &D);
+        bjj_mul_base(&p2, &table, &k, &A, &D);
         bjj_to_affine(&x1, &y1, &p1); bjj_to_affine(&x2, &y2, &p2);
         if (x1 != x2 || y1 != y2) return 0;
     }
