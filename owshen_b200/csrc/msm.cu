@@ -736,10 +736,9 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
         uint32_t n_out = (n_in + (1u << fan_log2) - 1) >> fan_log2;
         uint32_t threads = n_groups * n_out;
         const char* rn = sizeof(F) == 32 ? "k_reduce_level_g1" : "k_reduce_level_g2";
-        // OG_RED_SM: bit 0 = shared-memory running sums for G1, bit 1 = for G2 (A/B, profiles/r2_small_ab.md)
-        static const int red_sm = [] { const char* v = getenv("OG_RED_SM"); return v ? atoi(v) : -1; }();
-        const bool use_sm = red_sm >= 0 ? ((red_sm >> (sizeof(F) == 32 ? 0 : 1)) & 1) != 0 : RED_SM_DEFAULT<F>;
-        if (use_sm) {
+        // G1: running sums in registers, group operations out of line; G2: running sums in shared memory (profiles/r2_small_ab.md;
+        // the losing combination of each was removed from the library after the measurement)
+        if constexpr (RED_SM_DEFAULT<F>) {
             if (U_in) { auto k = k_reduce_level_sm<F, true>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
             else { auto k = k_reduce_level_sm<F, false>; OG_LAUNCHN(ctx, rn, k, (threads + 63) / 64, 64, 0, S_in, U_in, n_in, n_out, n_groups, w_log2, fan_log2, bufS[pp], bufU[pp]); }
         } else {
