@@ -798,7 +798,9 @@ __global__ void __launch_bounds__(128) k_horner(const XYZZ<F>* __restrict__ tota
     if (threadIdx.x == 0) { acc = XYZZ<F>::inf(); acc_inf = 1; }
     __syncthreads();
     for (int w = (int)n_windows - 1; w >= 0; w--) {
-        if (!acc_inf) {                                   // uniform: acc_inf is shared and only changes behind a barrier
+        const int inf_now = acc_inf;                      // every thread reads the flag BEFORE thread 0 may rewrite it below
+        __syncthreads();                                  // (racecheck found the missing barrier on the skip path)
+        if (!inf_now) {
             for (uint32_t k = 0; k < c; k++) {
                 if (lead) {
                     if (warp == 0) { F u = acc.y.dbl(); l1[0] = u.sqr(); }
