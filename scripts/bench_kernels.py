@@ -34,8 +34,20 @@ def hbm_peak():
 
 
 def fr_bytes(rng, n):
+    """n 248-bit values (always canonical), fast in bulk: inputs whose distribution does not matter (hash inputs, NTT data)."""
     raw = rng.randbytes(31 * n)
     return b"".join(raw[31 * i:31 * i + 31] + b"\0" for i in range(n))
+
+
+def fr_uniform(rng, n):
+    """n scalars uniform in [0, r) ("uniform 254-bit"): 254 random bits, rejected above the modulus.  The
+    248-bit generator above leaves the top window of an MSM with 8-bit digits -> 128 heavy buckets, which is not the workload."""
+    out = bytearray()
+    while len(out) < 32 * n:
+        v = rng.getrandbits(254)
+        if v < R:
+            out += v.to_bytes(32, "little")
+    return bytes(out)
 
 
 def dev(b, device):
@@ -106,9 +118,9 @@ def main():
         pts = dev(pts_host, device)
         outp = torch.empty(64 if curve == "g1" else 128, dtype=torch.uint8, device=device)
         fn_ = L.og_msm_g1_dev if curve == "g1" else L.og_msm_g2_dev
-        kinds = {"uniform": fr_bytes(rng, n)}
+        kinds = {"uniform": fr_uniform(rng, n)}
         if curve == "g1":
-            wl = bytearray(fr_bytes(rng, n))
+            wl = bytearray(fr_uniform(rng, n))
             for i in range(n):
                 u = rng.random()
                 if u < 0.6:
