@@ -163,3 +163,63 @@ def test_mirror_kvstore_matches_the_reference_shape():
     assert m.rollback() == {b"a": b"1", b"b": b"2", b"c": None}           # mirror.rs:19-27
     base.batch_put_raw(m.buffer().items())
     assert base.db == {b"a": b"9", b"c": b"3"}
+
+
+def test_random_insert_pop_rollback_sequences_against_the_spec_tree():
+    """Model-based: a random walk of insert_batch / pop_batch / rollback / reopen against a list of leaves and the
+    oracle's spec tree rebuilt from that list; roots, leaf counts and a sample path must agree after every operation,
+    and the store must hold no stale undo records."""
+    from hypothesis import given, settings, strategies as st
+
+    ops = st.lists(st.one_of(st.tuples(st.just("ins"), st.integers(1, 9)), st.tuples(st.just("pop"), st.just(0)),
+                             st.tuples(st.just("roll"), st.integers(0, 40)), st.tuples(st.just("reopen"), st.just(0))),
+                   min_size=1, max_size=14)
+
+    @settings(max_examples=25, deadline=None)
+    @given(ops, st.integers(0, 2**32 - 1))
+    def run(seq, seed):
+        rng = random.Random(seed)
+        ctx = OracleHashCtx()
+        store = RamKvStore()
+        depth = 5
+        t = api.MerkleTree(ctx, depth, store=store)
+        leaves, batches = [], []                      # model: the leaf list and the sizes of the live batches
+        for op, arg in seq:
+            if op == "ins":
+                n = min(arg, (1 << depth) - len(leaves))
+                if n == 0:
+                    with pytest.raises(OverflowError):
+                        t.insert(fr(1))
+                    continue
+                new = [rng.randrange(bn.R) for _ in range(n)]
+                t.insert_batch(new); leaves += new; batches.append(n)
+            elif op == "pop":
+                removed = t.pop_batch()
+                assert removed == (batches.pop() if batches else 0)
+                if removed:
+                    del leaves[-removed:]
+            elif op == "roll":
+                target = min(arg, len(leaves))
+                t.rollback(target)
+                del leaves[target:]
+                kept, acc = [], 0                     # batches shrink from the end; a partially kept batch is re-inserted
+                for b in batches:
+                    if acc + b <= target:
+                        kept.append(b); acc += b
+                    else:
+                        if target - acc:
+                            kept.append(target - acc)
+                        break
+                batches = kept
+            else:
+                t = api.MerkleTree(ctx, depth, store=store)
+            ref = mimc7.MerkleTree(depth)
+            for x in leaves:
+                ref.insert(x)
+            assert t.n_leaves == len(leaves) and t.root() == fr(ref.root()) and t.n_batches == len(batches)
+            if leaves:
+                i = rng.randrange(len(leaves))
+                assert t.path(i)[0] == b"".join(fr(x) for x in ref.path(i)[0])
+            deltas = [k for k in store.db if k.startswith(b"mt/delta")]
+            assert len(deltas) == len(batches)
+    run()
