@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(128, 8) k_bucket_acc_sm1(const Affine<Fq>* __r
 #ifdef OG_MSM_G2
 // G2 variant with the 256-byte accumulator in shared memory (16-byte chunks interleaved over the CTA's threads, so
 // every access is conflict-free): registers hold only the temporaries of one mixed addition, which buys resident
-// warps in a kernel whose top stall is the fixed-latency wait of the carry chains (OG_ACC_OCC_G2 = 14, 15, 16).
+// warps in a kernel whose top stall is the fixed-latency wait of the carry chains (4, 5 and 6 resident CTAs were measured
+// in round 1, profiles/r1_bucket_acc_smem_sweep.md; 6 won).
 struct SmAcc {
     uint4* base;    // [16 chunks][128 threads]
     __device__ __forceinline__ Fq2 ld(int coord) const {

@@ -268,7 +268,7 @@ int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t ba
     plans[np - 1].last = 1;
     // OG_NTT_TMA=1: intermediates pre-swizzled + TMA bulk tile loads in the non-first passes.  Measured equal in the prover (32.4 vs
     // 32.4 ms per step) and 0.6-3.6 % slower standalone (profiles/r2_ntt_tma_ab.md), hence not the default
-    static const int use_tma = [] { const char* e = getenv("OG_NTT_TMA"); return e ? atoi(e) : 0; }();
+    const int use_tma = [] { const char* e = getenv("OG_NTT_TMA"); return e ? atoi(e) : 0; }();     // read per call: tests toggle it
     for (int i = 0; i < np; i++) plans[i].tma = (use_tma && np > 1) ? 1 : 0;
     for (int i = 0; i < np; i++) {
         const PassPlan& p = plans[i];

@@ -127,6 +127,24 @@ def test_ntt_matches_oracle_all_modes(ctx):
         assert hashlib.sha256(got).hexdigest() == v["sha256"]
 
 
+def test_ntt_tma_tile_loads_match_plain_loads(ctx, monkeypatch):
+    """OG_NTT_TMA=1: intermediate buffers pre-swizzled, non-first passes fetch their tiles with cp.async.bulk + mbarrier.
+    Same bytes as the plain-load kernel and as the oracle, for two-pass and three-pass sizes, batched, all modes."""
+    rng = random.Random(2718)
+    for log_n, batch in ((11, 3), (13, 2), (15, 4), (21, 1)):
+        data = rand_fr_bytes(rng, batch << log_n)
+        for inverse, coset in ((False, False), (True, True), (False, True)):
+            monkeypatch.setenv("OG_NTT_TMA", "0")
+            plain = ctx.ntt(data, log_n, batch, inverse, coset)
+            monkeypatch.setenv("OG_NTT_TMA", "1")
+            tma = ctx.ntt(data, log_n, batch, inverse, coset)
+            assert tma == plain, (log_n, batch, inverse, coset)
+        if log_n <= 13:
+            one = data[:32 << log_n]
+            assert ctx.ntt(one, log_n, 1, False, True) == cport.ntt(one, False, True)
+    monkeypatch.delenv("OG_NTT_TMA")
+
+
 def test_ntt_properties_2_20(ctx):
     """Size-independent properties at n = 2^20: round trip and linearity (oracle-free)."""
     rng = random.Random(6)
