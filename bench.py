@@ -487,6 +487,16 @@ def main():
         # 10 field multiplications per G1 mixed add, 128 32x32->64 multiply-adds per multiplication
         wide_mads = madds_per_proof_g1 * batch * args.steps * 10 * 128
         wide_rate = wide_mads / (kms * 1e-3) if kms > 0 else 0.0
+        # arithmetic floor of the whole step: 32x32->64 multiply-adds of every arithmetic kernel by static count
+        # (G1 mixed add 8M+2S = 1280, G2 8 x 320 + 2 x 246 = 3052, XYZZ+XYZZ add 14M = 1792 / 4332 at 2.29 additions per bucket,
+        # NTT (m/2 log m - 0.75 m) x 128 per transform, 6 transforms per proof) against the carry-chain peak measured in this run
+        nb_of = lambda c: 1 << (c - 1)
+        cA, cB, cC = cbits("OG_C_A", 15), cbits("OG_C_B", 15), cbits("OG_C_C", 16)
+        log_m = info["log_m"]
+        per_proof = (madds_per_proof_g1 * 1280 + (n_supp + 2) * win(cB) * 3052
+                     + (nb_of(cA) + nb_of(cC)) * 2.29 * 1792 + nb_of(cB) * 2.29 * 4332
+                     + 6 * (m / 2 * log_m - 0.75 * m) * 128)
+        step_mads = per_proof * batch
         parity = None
         if not args.no_parity:
             try:      # the oracle is the checker here, never the thing measured
@@ -542,7 +552,13 @@ def main():
                      "frac": wide_rate / pipes["imad_wide_carry_chain_per_s"] if pipes["imad_wide_carry_chain_per_s"] else None,
                      "peak_imad_per_s": pipes["imad_per_s"], "peak_imad_wide_per_s": pipes["imad_wide_per_s"],
                      "note": "the binding roofline: 32x32->64 multiply-adds issued as carry chains (IMAD.WIDE.U32.X), peak measured "
-                             "by og_int_pipe_peaks on this GPU in this run; achieved = mixed adds x 10 field muls x 128 products"},
+                             "by og_int_pipe_peaks on this GPU in this run; achieved = mixed adds x 10 field muls x 128 products",
+                     "step": {"wide_mads_per_step": step_mads,
+                              "floor_ms": 1e3 * step_mads / pipes["imad_wide_carry_chain_per_s"] if pipes["imad_wide_carry_chain_per_s"] else None,
+                              "frac_of_step": (1e3 * step_mads / pipes["imad_wide_carry_chain_per_s"]) / (dev_ms / args.steps) if pipes["imad_wide_carry_chain_per_s"] else None,
+                              "note": "multiply-adds of the bucket accumulations, bucket reductions and NTTs of one step by static count / measured "
+                                      "carry-chain peak = the time the step would take if only the multiplier mattered; the sort, the witness chains "
+                                      "and the assembly are not arithmetic-bound and are not in the floor"}},
             "kernels": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in top[:12]},
             "cpu_baseline": cpu,
             "sharded_msm": sharded,
