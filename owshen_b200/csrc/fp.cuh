@@ -165,9 +165,29 @@ OG_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, bo
     E[0] = 0;                                         // dead from here on
 }
 
-// r = a * b * 2^-256 mod p   (a, b < p; r may alias a or b)
+// 2p as limbs (p < 2^254, so 2p < 2^255)
 template <class P>
-OG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+OG_HD constexpr uint32_t mod2(int i) { return (P::mod(i) << 1) | (i ? P::mod(i - 1) >> 31 : 0u); }
+
+// r = (r >= 2p) ? r - 2p : r     (r < 4p): the one conditional subtraction per round that keeps a chain of lazy products
+// (operands and results in [0, 2p), see mont_mul_lazy) from growing
+template <class P>
+OG_HD void cond_sub_2p(uint32_t* r) {
+    uint32_t t[8];
+    CC cc;
+    t[0] = sub_cc(r[0], mod2<P>(0), cc);
+#pragma unroll
+    for (int j = 1; j < 8; j++) t[j] = subc_cc(r[j], mod2<P>(j), cc);
+    uint32_t borrow = subc(0u, 0u, cc);
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = borrow ? r[j] : t[j];
+}
+
+// r = (a * b + m * p) / 2^256 with m < 2^256, i.e. r == a * b * 2^-256 (mod p) and r < a * b / 2^256 + p.  For a, b < 2p
+// that is r < (4p / 2^256 + 1) p < 1.76 p (p < 0.19 * 2^256): products of values in [0, 2p) stay in [0, 2p) without any final
+// subtraction, and no running sum leaves 2^288 (a + p < 2^256).  r may alias a or b.
+template <class P>
+OG_HD void mont_mul_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     uint32_t E[8], O[8];
     mont_row<P>(E, O, a, b[0], true);
     mont_row<P>(O, E, a, b[1], false);
@@ -182,6 +202,12 @@ OG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
     for (int j = 1; j < 7; j++) r[j] = addc_cc(E[j], O[j + 1], cc);
     r[7] = addc(E[7], 0u, cc);
+}
+
+// r = a * b * 2^-256 mod p, fully reduced   (a, b < p; r may alias a or b)
+template <class P>
+OG_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    mont_mul_lazy<P>(r, a, b);
     final_sub<P>(r);
 }
 
@@ -322,9 +348,9 @@ OG_HD void mont_redc_row(uint32_t* E, uint32_t* O, bool first, uint32_t t_in, ui
     E[0] = 0;
 }
 
-// r = T * 2^-256 mod p for T < 2^256 * p (any product of operands < 2p qualifies), result fully reduced
+// r = (T + m p) / 2^256 for T < 2^256 * p (any product of operands < 2p qualifies): r == T * 2^-256 (mod p), r < T / 2^256 + p
 template <class P>
-OG_HD void mont_reduce_wide(uint32_t* r, const uint32_t* T) {
+OG_HD void mont_reduce_wide_lazy(uint32_t* r, const uint32_t* T) {
     uint32_t E[8], O[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) { E[k] = T[k]; O[k] = 0; }
@@ -343,6 +369,12 @@ OG_HD void mont_reduce_wide(uint32_t* r, const uint32_t* T) {
 #pragma unroll
     for (int j = 1; j < 7; j++) r[j] = addc_cc(E[j], O[j + 1], cc);
     r[7] = addc(E[7], 0u, cc);
+}
+
+// r = T * 2^-256 mod p, fully reduced
+template <class P>
+OG_HD void mont_reduce_wide(uint32_t* r, const uint32_t* T) {
+    mont_reduce_wide_lazy<P>(r, T);
     final_sub<P>(r);
 }
 
@@ -374,6 +406,22 @@ struct alignas(32) Fp {
 #else
     OG_HD Fp sqr() const { Fp r; uint32_t T[16]; sqr_wide(T, l); mont_reduce_wide<P>(r.l, T); return r; }   // 36 + 64 products
 #endif
+
+    // lazy forms for long dependent chains (MiMC): values in [0, 2p), no final subtraction (bounds at mont_mul_lazy)
+    OG_HD static Fp mul_lazy(const Fp& a, const Fp& b) { Fp r; mont_mul_lazy<P>(r.l, a.l, b.l); return r; }
+    OG_HD Fp sqr_lazy() const { Fp r; uint32_t T[16]; sqr_wide(T, l); mont_reduce_wide_lazy<P>(r.l, T); return r; }
+    // a + b as integers (the caller knows the sum is below 2^256)
+    OG_HD static Fp add_raw(const Fp& a, const Fp& b) {
+        Fp r; CC cc;
+        r.l[0] = add_cc(a.l[0], b.l[0], cc);
+#pragma unroll
+        for (int j = 1; j < 7; j++) r.l[j] = addc_cc(a.l[j], b.l[j], cc);
+        r.l[7] = addc(a.l[7], b.l[7], cc);
+        return r;
+    }
+    // value < 4p -> [0, 2p)  /  value < 2p -> [0, p)
+    OG_HD Fp reduce_4p_to_2p() const { Fp r = *this; cond_sub_2p<P>(r.l); return r; }
+    OG_HD Fp reduce_2p_to_p() const { Fp r = *this; final_sub<P>(r.l); return r; }
 
     OG_HD friend Fp operator+(const Fp& a, const Fp& b) {
         Fp r; CC cc;

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "host_math.hpp"
 #include "mimc.cuh"
+#include "mimc_core.cuh"
 #include <stdlib.h>
 
 namespace og {
@@ -47,9 +48,11 @@ __device__ __forceinline__ Fr mimc7_hash(const Fr& x, const Fr& k, Fr* trace) {
     return r + k;
 }
 
-// MultiMiMC7([l, r], key 0): r1 = l + hash(l, 0); out = r1 + r + hash(r, r1)
+// MultiMiMC7([l, r], key 0): r1 = l + hash(l, 0); out = r1 + r + hash(r, r1).  The TRACE form (witness generation) stores
+// every fully reduced intermediate; the plain form is the lazy chain of mimc_core.cuh.
 template <bool TRACE>
 __device__ __forceinline__ Fr mimc7_hash2(const Fr& l, const Fr& r, Fr* trace1, Fr* trace2) {
+    if (!TRACE) return mimc7_hash2_lazy(l, r, [](int i) { return mimc_c(i); });
     Fr r1 = l + mimc7_hash<TRACE>(l, Fr::zero(), trace1);
     return r1 + r + mimc7_hash<TRACE>(r, r1, trace2);
 }

@@ -126,3 +126,24 @@ extern "C" void ht_wide(const uint8_t* a, const uint8_t* b, uint8_t* mul32, uint
         sqr_wide(T, x.l); mont_reduce_wide<FqParams>(r.l, T); store(sqr32 + 32 * i, r);
     }
 }
+
+// ---- lazy-reduction chain (mimc_core.cuh): the very code the MiMC7 kernels run, on the host ------------------------
+#include "host_math.hpp"
+#include "mimc_core.cuh"
+extern "C" void ht_mimc7_hash2_lazy(const uint8_t* l, const uint8_t* r, uint8_t* out, uint64_t n) {
+    static Fr c[MIMC_ROUNDS];
+    static bool init = false;
+    if (!init) { mimc7_round_constants(c); init = true; }
+    for (uint64_t i = 0; i < n; i++)
+        store(out + 32 * i, mimc7_hash2_lazy(load<Fr>(l + 32 * i), load<Fr>(r + 32 * i), [&](int k) { return c[k]; }));
+}
+// raw lazy ops on operands given as 256-bit integers < 2p in MONTGOMERY form (no conversion): out = raw limbs of the result.
+// op 0: mul_lazy, 1: sqr_lazy (of a), 2: add_raw + reduce_4p_to_2p
+extern "C" void ht_fr_lazy_raw(int op, const uint8_t* a, const uint8_t* b, uint8_t* out, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) {
+        Fr x, y, z;
+        memcpy(x.l, a + 32 * i, 32); memcpy(y.l, b + 32 * i, 32);
+        z = op == 0 ? Fr::mul_lazy(x, y) : (op == 1 ? x.sqr_lazy() : Fr::add_raw(x, y).reduce_4p_to_2p());
+        memcpy(out + 32 * i, z.l, 32);
+    }
+}

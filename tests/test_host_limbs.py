@@ -183,3 +183,37 @@ def test_field_limbs_hypothesis(h):
                 h.ht_wide(pack(xs), pack(ys), m, s, C.c_uint64(n))
                 assert cport.unfr(m.raw) == [a * b % mod for a, b in pairs] and cport.unfr(s.raw) == [a * a % mod for a in xs]
         check()
+
+
+def test_lazy_chain_ops_stay_below_2p(h):
+    """mul_lazy / sqr_lazy on operands anywhere in [0, 2p): congruent to a*b/2^256 and again below 2p (fp.cuh: mont_mul_lazy);
+    add_raw + reduce_4p_to_2p on operands whose sum is below 4p."""
+    rng = random.Random(11)
+    Rm = pow(2, -256, R)
+    edges = [0, 1, R - 1, R, R + 1, 2 * R - 1, 2 * R - 2, 2**254, 2**254 - 1, 2**255 - 1 if 2**255 - 1 < 2 * R else 2 * R - 1, (2 * R - 1) & ~0xFFFFFFFF]
+    xs = [rng.randrange(2 * R) for _ in range(2000)] + edges + edges
+    ys = [rng.randrange(2 * R) for _ in range(2000)] + edges + edges[::-1]
+    raw = lambda vs: b"".join(v.to_bytes(32, "little") for v in vs)
+    n = len(xs)
+    for op in (0, 1, 2):
+        out = C.create_string_buffer(32 * n)
+        h.ht_fr_lazy_raw(op, raw(xs), raw(ys), out, C.c_uint64(n))
+        got = [int.from_bytes(out.raw[32 * i:32 * i + 32], "little") for i in range(n)]
+        for a, b, g in zip(xs, ys, got):
+            if op == 0:
+                assert g < 2 * R and g % R == a * b * Rm % R, (a, b)
+            elif op == 1:
+                assert g < 2 * R and g % R == a * a * Rm % R, a
+            else:
+                assert g < 2 * R and g % R == (a + b) % R, (a, b)
+
+
+def test_mimc7_lazy_chain_matches_spec(h):
+    """mimc_core.cuh (one conditional subtraction per round, values in [0, 2p)) against the circomlib-style spec."""
+    from oracle import mimc7
+    rng = random.Random(12)
+    ls = [rng.randrange(R) for _ in range(40)] + [0, 0, R - 1, R - 1, 1, 2**253]
+    rs = [rng.randrange(R) for _ in range(40)] + [0, R - 1, 0, R - 1, 2, R - 2]
+    out = C.create_string_buffer(32 * len(ls))
+    h.ht_mimc7_hash2_lazy(cport.frs(ls), cport.frs(rs), out, C.c_uint64(len(ls)))
+    assert cport.unfr(out.raw) == [mimc7.hash2(a, b) for a, b in zip(ls, rs)]
