@@ -676,10 +676,73 @@ __global__ void __launch_bounds__(64) k_group_total(const XYZZ<F>* __restrict__ 
     out[g] = a;
 }
 
+// ---- 5b: the reduction above level 0 when there are FEW groups (one-shot MSMs: groups = windows) -------------------------
+// Levels 1.. of k_reduce_level then run a few thousand threads that each walk ~23 additions and up to 12 doublings in sequence:
+// four such levels were 0.7 of the 5.3 ms of a 2^20-point G1 MSM and 2 of the 6 ms of a 2^18-point G2 one.  With R_p, T_p the
+// level-0 sums of chunk p (2^f buckets each) a group's total is  sum_p (T_p + R_p) + 2^f sum_p p R_p,  and the weighted part
+// is taken bit by bit:  sum_p p R_p = sum_k 2^k Q_k,  Q_k = sum of the R_p whose index has bit k set.  The two plain sums and the
+// log2(n1) sums Q_k are independent tree reductions (one CTA each: a few strided additions per thread, then log2(threads) levels
+// in shared memory); one thread per group finishes with a Horner over the bits.  Depth ~16 + 28 group operations instead of ~120.
+constexpr uint32_t TAIL_THREADS = 128, TAIL_SLICE = 512;
+#ifndef OG_TAIL_MINB
+#define OG_TAIL_MINB 1
+#endif
+template <class F>
+__global__ void __launch_bounds__(TAIL_THREADS, OG_TAIL_MINB) k_tail_sums(const XYZZ<F>* __restrict__ R, const XYZZ<F>* __restrict__ T, uint32_t n1,
+                                                            uint32_t n_sums, uint32_t n_slices, XYZZ<F>* __restrict__ out) {
+    __shared__ XYZZ<F> a[TAIL_THREADS];
+    const uint32_t q = blockIdx.x, g = blockIdx.y, sl = blockIdx.z, tid = threadIdx.x;    // q = 0: sum T, 1: sum R, 2 + k: Q_k
+    const XYZZ<F>* src = (q == 0 ? T : R) + (size_t)g * n1;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (q < 2) {
+        const uint32_t lo = sl * TAIL_SLICE, hi = min(n1, lo + TAIL_SLICE);
+        for (uint32_t p = lo + tid; p < hi; p += TAIL_THREADS) xyzz_add_ni(&acc, &src[p]);
+    } else {                                              // the n1 / 2 indices with bit k set, enumerated densely: no idle lanes
+        const uint32_t k = q - 2, half = n1 >> 1, lo = sl * (TAIL_SLICE / 2), hi = min(half, lo + TAIL_SLICE / 2);
+        for (uint32_t j = lo + tid; j < hi; j += TAIL_THREADS) {
+            uint32_t p = ((j >> k) << (k + 1)) | (1u << k) | (j & ((1u << k) - 1));
+            xyzz_add_ni(&acc, &src[p]);
+        }
+    }
+    a[tid] = acc;
+    __syncthreads();
+    for (uint32_t s = TAIL_THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) xyzz_add_ni(&a[tid], &a[tid + s]);
+        __syncthreads();
+    }
+    if (tid == 0) out[((size_t)g * n_sums + q) * n_slices + sl] = a[0];
+}
+
+// total_g = sum T + sum R + 2^f * sum_k 2^k Q_k: the slices of every sum are added by a small tree, then one lane walks the
+// Horner over the bits (one CTA per group so that the groups sit on different SMs)
+template <class F>
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail_finish(const XYZZ<F>* __restrict__ partials, uint32_t n_sums, uint32_t n_slices, uint32_t f,
+                                                              XYZZ<F>* __restrict__ totals) {
+    __shared__ XYZZ<F> a[TAIL_THREADS];
+    const uint32_t tid = threadIdx.x, n = n_sums * n_slices;      // <= 128: n_sums <= 16 sums of <= 8 slices
+    if (tid < n) a[tid] = partials[(size_t)blockIdx.x * n + tid];
+    __syncthreads();
+    for (uint32_t s = n_slices / 2; s > 0; s >>= 1) {             // n_slices is a power of two; slice 0 of every sum collects
+        if (tid < n && (tid % n_slices) < s) xyzz_add_ni(&a[tid], &a[tid + s]);
+        __syncthreads();
+    }
+    if (tid) return;
+    XYZZ<F> v = XYZZ<F>::inf();
+    for (int k = (int)n_sums - 3; k >= 0; k--) {
+        xyzz_dbl_ni(&v);
+        xyzz_add_ni(&v, &a[(2 + k) * n_slices]);
+    }
+    for (uint32_t i = 0; i < f; i++) xyzz_dbl_ni(&v);
+    xyzz_add_ni(&v, &a[0]);
+    xyzz_add_ni(&v, &a[n_slices]);
+    totals[blockIdx.x] = v;
+}
+
 template <class F>
 static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t* d_sorted, const uint32_t* d_offsets,
                            const uint32_t* d_counts, uint32_t n_groups, uint32_t nb, uint64_t n_entries_max, XYZZ<F>* d_buckets,
-                           XYZZ<F>* d_lvl, uint32_t* d_heavy, uint32_t* d_perm, XYZZ<F>* d_totals, void* aff_scratch = nullptr) {
+                           XYZZ<F>* d_lvl, uint32_t* d_heavy, uint32_t* d_perm, XYZZ<F>* d_totals, void* aff_scratch = nullptr,
+                           bool few_groups = false) {
     uint32_t n_keys = n_groups * nb;
     constexpr int HT = sizeof(F) == 32 ? 256 : 128;
     OG_CUDA(ctx, cudaMemsetAsync(d_heavy, 0, sizeof(uint32_t), ctx->stream));
@@ -750,6 +813,23 @@ static int32_t msm_buckets(og_ctx* ctx, const Affine<F>* d_table, const uint32_t
         pp ^= 1;
         n_in = n_out;
         w_log2 += fan_log2;
+        if (few_groups && w_log2 == fan_log2 && n_in >= 64 && (n_in & (n_in - 1)) == 0) {
+            // one-shot MSM: everything above level 0 as independent tree sums + one Horner per group (5b above)
+            static const bool tail = [] { const char* v = getenv("OG_MSM_TAIL"); return !(v && v[0] == '0' && v[1] == 0); }();
+            if (tail) {
+                uint32_t n_bits = 0;
+                while ((1u << n_bits) < n_in) n_bits++;
+                const uint32_t n_sums = n_bits + 2, n_slices = (n_in + TAIL_SLICE - 1) / TAIL_SLICE;
+                if (n_sums * n_slices <= TAIL_THREADS) {
+                    XYZZ<F>* partials = bufS[pp];                           // the other ping-pong buffer: n_groups * n_in / 8 + 16 >= n_groups * n_sums * n_slices
+                    OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_tail_sums_g1" : "k_tail_sums_g2", k_tail_sums<F>, dim3(n_sums, n_groups, n_slices), TAIL_THREADS, 0,
+                               S_in, U_in, n_in, n_sums, n_slices, partials);
+                    OG_LAUNCHN(ctx, sizeof(F) == 32 ? "k_tail_finish_g1" : "k_tail_finish_g2", k_tail_finish<F>, n_groups, TAIL_THREADS, 0, partials, n_sums, n_slices,
+                               w_log2, d_totals);
+                    return OG_OK;
+                }
+            }
+        }
     } while (n_in > 1);
     OG_LAUNCH(ctx, k_group_total<F>, (n_groups + 63) / 64, 64, 0, S_in, U_in, n_groups, d_totals);
     return OG_OK;
@@ -791,8 +871,11 @@ size_t msm_aff_scratch_bytes_g2(uint64_t) { return 0; }
 //   level 3: m (s - x3), w y, zzz' = w zzz   with x3 = mm - 2s, y3 = m (s - x3) - w y
 template <class F>
 __global__ void __launch_bounds__(128) k_horner(const XYZZ<F>* __restrict__ totals, uint32_t n_windows, uint32_t c, uint8_t* __restrict__ out) {
+    // acc.y is PENDING after a doubling: y = yt - ywy; the warps that need it form it themselves, so a doubling is three
+    // barriers (one per dependency level) and no serial epilogue.  Who touches what: x is read in levels 1-2 and rewritten in
+    // level 3; zz only by warp 3 (level 2), zzz only by warp 2 (level 3); y is published by warp 0 in level 1.
     __shared__ XYZZ<F> acc;
-    __shared__ F l1[2], l2[4], l3[3];
+    __shared__ F l1v, l1xx, l2w, l2s, l2mm, yt, ywy;
     __shared__ int acc_inf;
     const int warp = threadIdx.x >> 5;
     const bool lead = (threadIdx.x & 31) == 0;
@@ -801,41 +884,35 @@ __global__ void __launch_bounds__(128) k_horner(const XYZZ<F>* __restrict__ tota
     for (int w = (int)n_windows - 1; w >= 0; w--) {
         const int inf_now = acc_inf;                      // every thread reads the flag BEFORE thread 0 may rewrite it below
         __syncthreads();                                  // (racecheck found the missing barrier on the skip path)
+        bool ypend = false;
         if (!inf_now) {
             for (uint32_t k = 0; k < c; k++) {
-                if (lead) {
-                    if (warp == 0) { F u = acc.y.dbl(); l1[0] = u.sqr(); }
-                    else if (warp == 1) l1[1] = acc.x.sqr();
+                if (lead) {                               // level 1: v = (2y)^2, xx = x^2
+                    if (warp == 0) { F y = ypend ? yt - ywy : acc.y; acc.y = y; F u = y.dbl(); l1v = u.sqr(); }
+                    else if (warp == 1) l1xx = acc.x.sqr();
                 }
                 __syncthreads();
-                if (lead) {
-                    F v = l1[0];
-                    if (warp == 0) { F u = acc.y.dbl(); l2[0] = u * v; }
-                    else if (warp == 1) l2[1] = acc.x * v;
-                    else if (warp == 2) { F xx = l1[1]; F m = xx.dbl() + xx; l2[2] = m.sqr(); }
-                    else l2[3] = v * acc.zz;
+                if (lead) {                               // level 2: w = 2y v, s = x v, mm = (3 xx)^2, zz' = v zz
+                    F v = l1v;
+                    if (warp == 0) { F u = acc.y.dbl(); l2w = u * v; }
+                    else if (warp == 1) l2s = acc.x * v;
+                    else if (warp == 2) { F xx = l1xx; F m = xx.dbl() + xx; l2mm = m.sqr(); }
+                    else acc.zz = v * acc.zz;
                 }
                 __syncthreads();
-                if (lead) {
-                    F s = l2[1];
-                    F x3 = l2[2] - s.dbl();
-                    if (warp == 0) { F xx = l1[1]; F m = xx.dbl() + xx; l3[0] = m * (s - x3); }
-                    else if (warp == 1) l3[1] = l2[0] * acc.y;
-                    else if (warp == 2) l3[2] = l2[0] * acc.zzz;
+                if (lead) {                               // level 3: m (s - x3), w y, zzz' = w zzz, x3
+                    if (warp == 0) { F s = l2s; F x3 = l2mm - s.dbl(); F xx = l1xx; F m = xx.dbl() + xx; yt = m * (s - x3); }
+                    else if (warp == 1) ywy = l2w * acc.y;
+                    else if (warp == 2) acc.zzz = l2w * acc.zzz;
+                    else { F s = l2s; acc.x = l2mm - s.dbl(); }
                 }
                 __syncthreads();
-                if (threadIdx.x == 0) {
-                    F s = l2[1];
-                    acc.x = l2[2] - s.dbl();
-                    acc.y = l3[0] - l3[1];
-                    acc.zz = l2[3];
-                    acc.zzz = l3[2];
-                }
-                __syncthreads();
+                ypend = true;
             }
         }
         if (threadIdx.x == 0) {
             XYZZ<F> a = acc;
+            if (ypend) a.y = yt - ywy;
             xyzz_add_ni(&a, &totals[w]);
             acc = a;
             acc_inf = a.is_inf() ? 1 : 0;
@@ -893,7 +970,7 @@ static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sc
         if (v && atoi(v) > 0) { aff = ctx->slot(S_MSM_AFF, aff_scratch_bytes_t<F>(n_keys)); if (!aff) return OG_E_NOMEM; }
     }
 #endif
-    OG_TRY((msm_buckets<F>(ctx, pts, sorted, offsets, counts, W, nb, n * W, buckets, lvl, heavy, cursor, totals, aff)));
+    OG_TRY((msm_buckets<F>(ctx, pts, sorted, offsets, counts, W, nb, n * W, buckets, lvl, heavy, cursor, totals, aff, true)));
     OG_LAUNCH(ctx, k_horner<F>, 1, 128, 0, totals, W, c, d_out);
     return OG_OK;
 }

@@ -38,5 +38,10 @@ proofs, pub = ob.prove(PK, fr(b), fr(b), fr(b), fr(b), [rng.randrange(2) for _ i
 assert all(ob.verify(vk, pub[96 * i:96 * i + 96], proofs[256 * i:256 * i + 256]) for i in range(b))
 p2 = ctx.g2_generator_mul(fr(1)) * 300
 ctx.msm_g2(p2, (5).to_bytes(32, "little") * 300)
+# later in round 2: reduction tail of one-shot MSMs (k_tail_sums / k_tail_finish need >= 512 buckets per window, i.e. >= 2^13 points),
+# three-barrier Horner, lazy MiMC chain (covered by merkle_paths above)
+os.environ.pop("OG_CHUNK"); os.environ.pop("OG_LANES")
+pts = ctx.g1_generator_mul(fr(8192)); ctx.msm_g1(pts, fr(8192))
+pts = ctx.g2_generator_mul(fr(8192)); ctx.msm_g2(pts, fr(8192))
 PK.close(); ctx.close()
 print("sanitize workload done")
