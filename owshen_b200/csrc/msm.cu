@@ -12,6 +12,7 @@
 // All arithmetic is 8x32-bit Montgomery limbs in registers (fp.cuh); the kernels are bound by the
 // integer multiply-add pipe, not HBM: a G1 mixed add moves 64 B + 4 B and costs ~3.5k instructions.
 #include "msm.cuh"
+#include "glv.cuh"
 #include <stdlib.h>
 // Compiled twice: -DOG_MSM_G1 (G1 instantiations + the curve-independent sort) and -DOG_MSM_G2.
 #if !defined(OG_MSM_G1) && !defined(OG_MSM_G2)
@@ -929,6 +930,39 @@ __global__ void __launch_bounds__(128) k_horner(const XYZZ<F>* __restrict__ tota
     }
 }
 
+#ifdef OG_MSM_G1
+// GLV front end of the one-shot G1 MSM (glv.cuh): (P_i, k_i) -> (+-P_i, |k1_i|) at index i and (+-phi(P_i), |k2_i|) at index n + i;
+// the signs go into the points.  phi(P_i) is MATERIALISED: applying beta at fetch time instead (entries >= n standing for phi of
+// point index - n, signs in the scalars) keeps the table at 64 MB but costs a product per phi entry in the accumulation kernel and
+// measured 3.61 vs 3.27 ms of accumulation at 2^20 points (profiles/r2_msm_oneshot_breakdown.md)
+__global__ void __launch_bounds__(128) k_glv_expand(const uint8_t* __restrict__ scalars, uint64_t n, Fq beta, Affine<Fq>* __restrict__ pts,
+                                                    uint32_t* __restrict__ sc2, int* flag) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(scalars + 32 * i);
+    uint32_t k[8], m1[8], m2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = sp[j];
+    if (!Fr::canonical_lt_mod(k)) {
+        atomicOr(flag, 1);
+#pragma unroll
+        for (int j = 0; j < 8; j++) k[j] = 0;
+    }
+    bool n1, n2;
+    glv_decompose(k, m1, n1, m2, n2);
+    Affine<Fq> p = pts[i];
+    const Fq yn = p.y.neg();
+    Affine<Fq> q{p.x * beta, n2 ? yn : p.y};          // (0, 0) stays (0, 0)
+    if (n1) p.y = yn;
+    pts[i] = p;
+    pts[n + i] = q;
+    uint32_t* o1 = sc2 + 8 * i;
+    uint32_t* o2 = sc2 + 8 * (n + i);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { o1[j] = m1[j]; o2[j] = m2[j]; }
+}
+#endif
+
 static uint32_t pick_window(uint64_t n) {
     uint32_t lg = 0;
     while ((1ull << (lg + 1)) <= n) lg++;
@@ -944,7 +978,13 @@ static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sc
     if (n >= (1ull << 28)) return OG_E_INVALID;
     if (!aligned32(d_points) || !aligned32(d_scalars)) return OG_E_INVALID;
     if (n == 0) { OG_CUDA(ctx, cudaMemsetAsync(d_out, 0, PB, ctx->stream)); return OG_OK; }
-    uint32_t c = pick_window(n), W = msm_windows(c), nb = 1u << (c - 1);
+    // G1: GLV halves the scalar length (2n points, 127-bit scalars): same bucket additions, half the windows to reduce and half
+    // the sequential doublings of the Horner (OG_GLV=0 switches it off for A/B)
+    static const bool glv_on = [] { const char* v = getenv("OG_GLV"); return !(v && v[0] == '0' && v[1] == 0); }();
+    const bool glv = sizeof(F) == 32 && glv_on && n >= 1024;
+    const uint64_t n_in = n;
+    if (glv) n = 2 * n;
+    uint32_t c = pick_window(n), W = glv ? (128 + c - 1) / c : msm_windows(c), nb = 1u << (c - 1);
     uint32_t n_keys = W * nb;
     OG_SLOT(ctx, pts, Affine<F>, S_MSM_POINTS, sizeof(Affine<F>) * n);
     OG_SLOT(ctx, counts, uint32_t, S_MSM_COUNTS, 4 * (size_t)n_keys);
@@ -955,7 +995,17 @@ static int32_t msm_dev(og_ctx* ctx, const uint8_t* d_points, const uint8_t* d_sc
     OG_SLOT(ctx, lvl, XYZZ<F>, S_MSM_SEG, sizeof(XYZZ<F>) * msm_lvl_elems(W, nb));
     OG_SLOT(ctx, heavy, uint32_t, S_MSM_HEAVY, 4 * (2 * (size_t)n_keys + 4));
     OG_SLOT(ctx, totals, XYZZ<F>, S_MSM_OUT, sizeof(XYZZ<F>) * W);
-    OG_LAUNCH(ctx, k_points_to_mont<F>, (unsigned)((n + 127) / 128), 128, 0, d_points, n, pts, ctx->d_flag);
+    OG_LAUNCH(ctx, k_points_to_mont<F>, (unsigned)((n_in + 127) / 128), 128, 0, d_points, n_in, pts, ctx->d_flag);
+#ifdef OG_MSM_G1
+    if (glv) {
+        OG_SLOT(ctx, sc2, uint32_t, S_MSM_SCALARS, 32 * (size_t)n);
+        uint32_t bl[8];
+        for (int i = 0; i < 8; i++) bl[i] = Glv::beta(i);
+        const Fq beta = Fq::from_canonical(bl);
+        OG_LAUNCH(ctx, k_glv_expand, (unsigned)((n_in + 127) / 128), 128, 0, d_scalars, n_in, beta, reinterpret_cast<Affine<Fq>*>(pts), sc2, ctx->d_flag);
+        d_scalars = reinterpret_cast<const uint8_t*>(sc2);
+    }
+#endif
     DigitPlan plan;
     plan.scalars = reinterpret_cast<const uint32_t*>(d_scalars);
     plan.n = n; plan.scalar_stride = 0; plan.n_problems = 1;

@@ -147,3 +147,17 @@ extern "C" void ht_fr_lazy_raw(int op, const uint8_t* a, const uint8_t* b, uint8
         memcpy(out + 32 * i, z.l, 32);
     }
 }
+
+// ---- GLV decomposition (glv.cuh): out = |k1| (32 B) | |k2| (32 B) | sign bits (1 B: bit 0 = k1 < 0, bit 1 = k2 < 0) per scalar
+#include "glv.cuh"
+extern "C" void ht_glv_decompose(const uint8_t* ks, uint8_t* out, uint64_t n) {
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t k[8], a[8], b[8];
+        bool n1, n2;
+        memcpy(k, ks + 32 * i, 32);
+        glv_decompose(k, a, n1, b, n2);
+        memcpy(out + 65 * i, a, 32); memcpy(out + 65 * i + 32, b, 32);
+        out[65 * i + 64] = (uint8_t)((n1 ? 1 : 0) | (n2 ? 2 : 0));
+    }
+}
+extern "C" void ht_glv_beta(uint8_t* out) { for (int i = 0; i < 8; i++) { uint32_t v = Glv::beta(i); memcpy(out + 4 * i, &v, 4); } }

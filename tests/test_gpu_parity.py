@@ -159,6 +159,30 @@ def test_ntt_properties_2_20(ctx):
     assert fa0 == cport.ntt(a)            # and the oracle agrees at full size
 
 
+def test_msm_g1_glv_edge_scalars(ctx):
+    """One-shot G1 MSMs of >= 1024 points run the GLV front end (glv.cuh): k = k1 + k2 lambda with the signs folded into the
+    points.  Scalars around the lattice constants, the 2^127 boundary and r, points at infinity, P / -P pairs that cancel."""
+    rng = random.Random(77)
+    LAM = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    A1, A2 = 9931322734385697763, 147946756881789319010696353538189108491
+    special = [0, 1, 2, R - 1, R - 2, LAM, R - LAM, LAM - 1, LAM + 1, LAM * LAM % R, 2**127, 2**127 - 1, 2**127 + 1, 2**128, 2**126,
+               A1, A2, R - A1, R - A2, (A1 * LAM) % R, (A2 * LAM) % R, R // 2, R // 2 + 1, 2**253, 2**64, 2**64 - 1, 2**32]
+    n = 3000
+    sc = [special[i % len(special)] if i % 3 else rng.randrange(R) for i in range(n)]
+    pts = bytearray(rand_g1(rng, n))
+    for i in range(0, 200, 2):                           # P, -P with the same scalar: the pair cancels
+        x, y = pts[64 * i:64 * i + 32], int.from_bytes(pts[64 * i + 32:64 * i + 64], "little")
+        pts[64 * (i + 1):64 * (i + 2)] = x + ((bn.P - y) % bn.P).to_bytes(32, "little")
+        sc[i + 1] = sc[i]
+    for i in (5, 1023, 1024, 2999):
+        pts[64 * i:64 * (i + 1)] = bytes(64)             # infinity
+    pts = bytes(pts)
+    assert ctx.msm_g1(pts, cport.frs(sc)) == cport.g1_msm(pts, cport.frs(sc))
+    for k in special:                                    # every special scalar on every point at once: sum = k * (sum of points)
+        m = 1024
+        assert ctx.msm_g1(pts[:64 * m], cport.frs([k] * m)) == cport.g1_msm(pts[:64 * m], cport.frs([k] * m)), hex(k)
+
+
 def test_msm_edge_cases(ctx):
     rng = random.Random(7)
     for n in (0, 1, 2, 3, 33, 255, 1024, 5000):

@@ -217,3 +217,30 @@ def test_mimc7_lazy_chain_matches_spec(h):
     out = C.create_string_buffer(32 * len(ls))
     h.ht_mimc7_hash2_lazy(cport.frs(ls), cport.frs(rs), out, C.c_uint64(len(ls)))
     assert cport.unfr(out.raw) == [mimc7.hash2(a, b) for a, b in zip(ls, rs)]
+
+
+def test_glv_decomposition(h):
+    """glv.cuh: k = k1 + k2 * lambda (mod r), |k1|, |k2| < 2^127, and (beta x, y) = lambda (x, y) on G1 -- against big integers
+    and the oracle's group law."""
+    LAM = 0xb3c4d79d41a917585bfc41088d8daaa78b17ea66b99c90dd
+    o = C.create_string_buffer(32); h.ht_glv_beta(o)
+    beta = int.from_bytes(o.raw, "little")
+    assert pow(beta, 3, P) == 1 and beta != 1 and pow(LAM, 3, R) == 1 and LAM != 1
+    rng = random.Random(21)
+    for k in (1, 2, 12345, rng.randrange(R)):
+        g = bn.g1_mul(bn.G1_GEN, k)
+        assert bn.g1_mul(g, LAM) == (beta * g[0] % P, g[1])
+    ks = [0, 1, 2, R - 1, R - 2, R // 2, R // 2 + 1, LAM, R - LAM, LAM - 1, 2**253, 2**128, 2**127, 2**127 - 1, 2**64] + [rng.randrange(R) for _ in range(20000)]
+    ks += [rng.randrange(2**b) for b in (1, 8, 33, 64, 65, 127, 128, 129, 200, 250) for _ in range(50)]
+    out = C.create_string_buffer(65 * len(ks))
+    h.ht_glv_decompose(b"".join(k.to_bytes(32, "little") for k in ks), out, C.c_uint64(len(ks)))
+    worst = 0
+    for i, k in enumerate(ks):
+        rec = out.raw[65 * i:65 * i + 65]
+        m1, m2, sg = int.from_bytes(rec[:32], "little"), int.from_bytes(rec[32:64], "little"), rec[64]
+        k1 = -m1 if sg & 1 else m1
+        k2 = -m2 if sg & 2 else m2
+        assert (k1 + k2 * LAM - k) % R == 0, k
+        assert m1 < 2**127 and m2 < 2**127, k
+        worst = max(worst, m1, m2)
+    assert worst < int(0.56 * 2**127)
