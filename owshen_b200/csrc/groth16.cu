@@ -436,8 +436,8 @@ static int32_t prove_chunk(og_ctx* ctx, const og_pk* pk, ChunkBufs& b, const Wit
     OG_LAUNCH(ctx, k_extras, (B + 127) / 128, 128, 0, d_rs + 64ull * off, B, pk->n_vars, b.w_stride, W, rs_m, ctx->d_flag);
     CsrDev A{pk->a_ptr, pk->a_col, pk->a_val}, Bm{pk->b_ptr, pk->b_col, pk->b_val};
     OG_LAUNCH(ctx, k_abc, dim3((m + 127) / 128, B), 128, 0, A, Bm, pk->n_constraints, pk->n_pub, pk->log_m, W, b.w_stride, B, b.abc);
-    OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3 * B, 1, 0));
-    OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3 * B, 0, 1));
+    OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3 * B, 1, 0, 1));      // 1/n folded into ...
+    OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3 * B, 0, 1, 2));      // ... the coset factors of the forward transform
     uint32_t mx = n_priv > pk->n_supp ? n_priv : pk->n_supp;
     OG_LAUNCH(ctx, k_compose, dim3((mx + 127) / 128, B), 128, 0, W, b.w_stride, rs_m, pk->supp, pk->n_supp, pk->n_vars, pk->n_pub, m,
               b.bsc, b.bsc_stride, b.csc, b.csc_stride);
@@ -524,8 +524,8 @@ int32_t h_evals_dev(og_ctx* ctx, const og_pk* pk, const uint8_t* d_wit, uint8_t*
     OG_LAUNCH(ctx, k_witness_in, (pk->n_vars + 127) / 128, 128, 0, d_wit, 1, pk->n_vars, b.w_stride, b.W, ctx->d_flag);
     CsrDev A{pk->a_ptr, pk->a_col, pk->a_val}, Bm{pk->b_ptr, pk->b_col, pk->b_val};
     OG_LAUNCH(ctx, k_abc, dim3((m + 127) / 128, 1), 128, 0, A, Bm, pk->n_constraints, pk->n_pub, pk->log_m, b.W, b.w_stride, 1, b.abc);
-    OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3, 1, 0));
-    OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3, 0, 1));
+    OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3, 1, 0, 1));
+    OG_TRY(ntt_mont_dev(ctx, b.abc, b.ntt_tmp, pk->log_m, 3, 0, 1, 2));
     OG_LAUNCH(ctx, k_pointwise, dim3((m + 127) / 128, 1), 128, 0, b.abc, pk->log_m, 1, b.csc, b.csc_stride, n_priv + pk->n_supp);
     return mimc_from_mont_dev(ctx, b.csc + n_priv + pk->n_supp, m, d_out);
 }

@@ -21,6 +21,7 @@ namespace og {
 struct NttTables {
     uint32_t log_n;
     Fr* d_t2;      // omega_{2n}^j, j < n, Montgomery form
+    Fr* d_t2n;     // omega_{2n}^j / n: coset factors that also carry the 1/n of a preceding inverse transform (ntt_mont_dev: fold)
     Fr n_inv;      // 1/n, Montgomery form
 };
 
@@ -35,6 +36,11 @@ __global__ void __launch_bounds__(256) k_ntt_table(Fr g, uint64_t n, Fr* __restr
     t2[j] = acc;
 }
 
+__global__ void __launch_bounds__(256) k_ntt_table_scaled(const Fr* __restrict__ t2, Fr n_inv, uint64_t n, Fr* __restrict__ t2n) {
+    uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) t2n[j] = t2[j] * n_inv;
+}
+
 // omega_{2n}^(+-j), 0 <= j < n
 __device__ __forceinline__ Fr tw2(const Fr* __restrict__ t2, uint32_t n, uint32_t j, bool inverse) {
     if (!inverse || j == 0) return t2[j];
@@ -47,6 +53,8 @@ struct PassPlan {
     uint32_t K;         // stages in this pass
     uint32_t L;         // log2 of consecutive columns per tile (0 in the first pass)
     uint32_t first, last, inverse, coset;
+    uint32_t fold;      // 1: inverse transform whose 1/n is left to the next transform; 2: forward coset transform that applies it
+                        // (its coset factors come from t2n = t2 / n): one product per element fewer for the pair (groth16.cu)
     uint32_t tma;       // intermediate buffers hold elements with bit 2 of their index set with the two 16-byte halves swapped, and
                         // non-first passes fetch their tile with cp.async.bulk (see k_ntt_pass2)
 };
@@ -100,7 +108,7 @@ __device__ __forceinline__ void sm_put(uint4* sm, uint32_t e, const Fr& v) {
 // 3 resident CTAs of 256 threads per SM (80 registers): measured 35.7 -> 31.9 ms per 1024 proofs against 2 CTAs,
 // 4 CTAs (64 registers) was equal
 __global__ void __launch_bounds__(256, 3) k_ntt_pass2(PassPlan P, const Fr* __restrict__ in, Fr* __restrict__ out,
-                                                   const Fr* __restrict__ t2, Fr n_inv) {
+                                                   const Fr* __restrict__ t2, const Fr* __restrict__ t2n, Fr n_inv) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     uint4* sm = reinterpret_cast<uint4*>(smem_raw);
     const uint32_t n = 1u << P.log_n;
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass2(PassPlan P, const Fr* __re
             if (P.first) {
                 uint32_t j = bitrev(i, P.log_n);
                 v = src[j];
-                if (P.coset && !P.inverse) v = v * t2[j];
+                if (P.coset && !P.inverse) v = v * (P.fold == 2 ? t2n[j] : t2[j]);
             } else {
                 v = src[i];
             }
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__(256, 3) k_ntt_pass2(PassPlan P, const Fr* __re
         uint32_t i = base | (k << B0) | lo;
         Fr v = sm_get(sm, e);
         if (P.last && P.inverse) {
-            v = v * n_inv;
+            if (P.fold != 1) v = v * n_inv;
             if (P.coset) v = v * tw2(t2, n, i, true);
         }
         if (P.tma && !P.last) {                         // intermediate buffer: halves swapped where bit 2 of the index is set
@@ -226,6 +234,8 @@ static int32_t get_tables(og_ctx* ctx, uint32_t log_n, NttTables** out) {
         uint32_t nn[8] = {0};
         nn[log_n >> 5] = 1u << (log_n & 31);
         T->n_inv = Fr::from_canonical(nn).inv();
+        OG_CUDA(ctx, cudaMalloc(&T->d_t2n, sizeof(Fr) * n));
+        OG_LAUNCH(ctx, k_ntt_table_scaled, (unsigned)((n + 255) / 256), 256, 0, T->d_t2, T->n_inv, n, T->d_t2n);
         ctx->ntt[log_n] = T;
     }
     *out = ctx->ntt[log_n];
@@ -236,12 +246,14 @@ int32_t ntt_prepare(og_ctx* ctx, uint32_t log_n) { NttTables* T; return get_tabl
 
 void ntt_free_tables(og_ctx* ctx) {
     for (int i = 0; i < 32; i++)
-        if (ctx->ntt[i]) { cudaFree(ctx->ntt[i]->d_t2); delete ctx->ntt[i]; ctx->ntt[i] = nullptr; }
+        if (ctx->ntt[i]) { cudaFree(ctx->ntt[i]->d_t2); cudaFree(ctx->ntt[i]->d_t2n); delete ctx->ntt[i]; ctx->ntt[i] = nullptr; }
 }
 
 // In-place on `data` (Montgomery form); `tmp` must hold batch * n elements when log_n > 10.
-int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t batch, int inverse, int coset) {
+// fold = 1 (inverse, no coset): the 1/n is NOT applied; fold = 2 (forward coset): the coset scaling also applies that 1/n.
+int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t batch, int inverse, int coset, int fold) {
     if (batch == 0) return OG_OK;
+    if ((fold == 1 && !(inverse && !coset)) || (fold == 2 && !(!inverse && coset)) || fold < 0 || fold > 2) return OG_E_INVALID;
     NttTables* T;
     OG_TRY(get_tables(ctx, log_n, &T));
     if (log_n == 0) {
@@ -253,7 +265,7 @@ int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t ba
     uint32_t done = 0;
     while (done < log_n) {
         PassPlan p;
-        p.log_n = log_n; p.s0 = done + 1; p.inverse = inverse; p.coset = coset; p.first = (done == 0); p.last = 0; p.tma = 0;
+        p.log_n = log_n; p.s0 = done + 1; p.inverse = inverse; p.coset = coset; p.first = (done == 0); p.last = 0; p.tma = 0; p.fold = (uint32_t)fold;
         if (done == 0) { p.K = log_n < 10 ? log_n : 10; p.L = 0; }
         else {
             p.L = done < 3 ? done : 3;
@@ -280,7 +292,7 @@ int32_t ntt_mont_dev(og_ctx* ctx, Fr* data, Fr* tmp, uint32_t log_n, uint32_t ba
         uint32_t threads = tile / 4 < 32 ? 32 : (tile / 4 > 256 ? 256 : tile / 4);
         // the swizzle permutes chunks inside groups of 8 elements: pad tiny tiles up to one group
         size_t smem = (tile < 8 ? 8 : tile) * sizeof(Fr);
-        OG_LAUNCHN(ctx, "k_ntt_pass", k_ntt_pass2, grid, threads, smem, p, src, dst, T->d_t2, T->n_inv);
+        OG_LAUNCHN(ctx, "k_ntt_pass", k_ntt_pass2, grid, threads, smem, p, src, dst, T->d_t2, T->d_t2n, T->n_inv);
     }
     return OG_OK;
 }
