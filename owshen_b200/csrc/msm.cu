@@ -318,7 +318,10 @@ struct SmAcc1 {
 
 // 8 CTAs of 128 threads per SM (64 registers); only the next 4-byte ENTRY is read ahead, the 64-byte gather is
 // covered by the other warps (measured against 6/7 CTAs and against a prefetched point: profiles/r1_bucket_acc_smem_sweep.md)
-__global__ void __launch_bounds__(128, 8) k_bucket_acc_sm1(const Affine<Fq>* __restrict__ table, const uint32_t* __restrict__ sorted,
+#ifndef OG_ACC1_MINB
+#define OG_ACC1_MINB 8
+#endif
+__global__ void __launch_bounds__(128, OG_ACC1_MINB) k_bucket_acc_sm1(const Affine<Fq>* __restrict__ table, const uint32_t* __restrict__ sorted,
                                                         const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                                         uint32_t n_keys, uint32_t cap, XYZZ<Fq>* __restrict__ buckets,
                                                         uint32_t* __restrict__ heavy, const uint32_t* __restrict__ perm) {
