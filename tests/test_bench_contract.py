@@ -25,3 +25,16 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_launch_list_tool_reads_the_committed_ncu_csv(tmp_path):
+    """tools/launch_list_summary.py turns the committed ncu launch list into the table under profiles/: the dominant kernel of
+    the bench command must come out on top (this is the evidence the roofline share is checked against)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "ll.md"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "launch_list_summary.py"),
+                    os.path.join(root, "profiles", "r2_launches_bench_steps2.csv"), str(out), "t"], check=True)
+    rows = [l for l in out.read_text().splitlines() if l.startswith("| `")]
+    assert rows and rows[0].startswith("| `k_bucket_acc_sm1"), rows[:2]
