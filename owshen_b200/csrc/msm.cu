@@ -318,6 +318,24 @@ struct SmAcc1 {
 
 // 8 CTAs of 128 threads per SM (64 registers); only the next 4-byte ENTRY is read ahead, the 64-byte gather is
 // covered by the other warps (measured against 6/7 CTAs and against a prefetched point: profiles/r1_bucket_acc_smem_sweep.md)
+// the two squarings of a mixed addition through ONE out-of-line copy of the wide squarer (8 registers in, 8 out): with the squarer
+// inlined twice next to eight inlined products the kernel outgrew the instruction cache (ncu: 12.7 % of the warp samples waiting
+// for instructions after the wide squarer replaced the interleaved one, profiles/r2_small_ab.md)
+#ifndef OG_SQR_CALL
+#define OG_SQR_CALL 1
+#endif
+#if OG_SQR_CALL
+static __device__ __noinline__ Fq fq_sqr_call(Fq a) { return a.sqr(); }
+#define OG_ACC_SQR(x) fq_sqr_call(x)
+#else
+#define OG_ACC_SQR(x) (x).sqr()
+#endif
+#if defined(OG_MUL_CALL) && OG_MUL_CALL      // A/B: the eight products out of line as well
+static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { return a * b; }
+#define OG_ACC_MUL(x, y) fq_mul_call((x), (y))
+#else
+#define OG_ACC_MUL(x, y) ((x) * (y))
+#endif
 #ifndef OG_ACC1_MINB
 #define OG_ACC1_MINB 8
 #endif
@@ -345,22 +363,22 @@ __global__ void __launch_bounds__(128, OG_ACC1_MINB) k_bucket_acc_sm1(const Affi
         e = en;
         if (q.is_inf()) continue;
         if (inf) { A.st(0, q.x); A.st(1, q.y); A.st(2, Fq::one()); A.st(3, Fq::one()); inf = false; continue; }
-        Fq p = q.x * A.ld(2) - A.ld(0);
-        Fq r = q.y * A.ld(3) - A.ld(1);
+        Fq p = OG_ACC_MUL(q.x, A.ld(2)) - A.ld(0);
+        Fq r = OG_ACC_MUL(q.y, A.ld(3)) - A.ld(1);
         if (p.is_zero()) {
             if (r.is_zero()) { XYZZ<Fq> d = XYZZ<Fq>::dbl_affine(q); A.st(0, d.x); A.st(1, d.y); A.st(2, d.zz); A.st(3, d.zzz); }
             else inf = true;
             continue;
         }
         // ordered so that few temporaries are live at a time: zz and zzz are updated as soon as pp / ppp exist
-        Fq pp = p.sqr();
-        A.st(2, A.ld(2) * pp);
-        Fq ppp = p * pp;
-        A.st(3, A.ld(3) * ppp);
-        Fq q1 = A.ld(0) * pp;
-        Fq x3 = r.sqr() - ppp - q1.dbl();
+        Fq pp = OG_ACC_SQR(p);
+        A.st(2, OG_ACC_MUL(A.ld(2), pp));
+        Fq ppp = OG_ACC_MUL(p, pp);
+        A.st(3, OG_ACC_MUL(A.ld(3), ppp));
+        Fq q1 = OG_ACC_MUL(A.ld(0), pp);
+        Fq x3 = OG_ACC_SQR(r) - ppp - q1.dbl();
         A.st(0, x3);
-        A.st(1, r * (q1 - x3) - A.ld(1) * ppp);
+        A.st(1, OG_ACC_MUL(r, q1 - x3) - OG_ACC_MUL(A.ld(1), ppp));
     }
     buckets[key] = inf ? XYZZ<Fq>::inf() : XYZZ<Fq>{A.ld(0), A.ld(1), A.ld(2), A.ld(3)};
 }
